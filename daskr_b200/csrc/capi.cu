@@ -1,0 +1,703 @@
+// capi.cu -- the extern "C" boundary (include/daskr_b200.h): context, setup, built-in
+// problem callbacks, micro-API, NCCL plumbing, profiling.
+#include "dkb_internal.h"
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+#include <algorithm>
+
+DkbCtx *g_ctx = nullptr;
+static char g_err[512] = "";
+
+int dkb_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (g_ctx) strncpy(g_ctx->err, g_err, sizeof(g_ctx->err) - 1);
+    return code;
+}
+
+// Void code paths (kernel launch helpers, Fortran-style subroutines) cannot return a status;
+// a CUDA error there is fatal and must be loud -- there is no CPU fallback to hide behind.
+void dkb_cuda_check(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        fprintf(stderr, "daskr_b200: CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+        abort();
+    }
+}
+
+// ---------------------------------------------------------------- NCCL (dlopen'ed: single-GPU
+// use never needs the library; with torch in the process this binds to the copy torch loaded)
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+enum { NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
+static struct {
+    void *lib;
+    int (*GetUniqueId)(nccl_uid *);
+    int (*CommInitRank)(nccl_comm *, int, nccl_uid, int);
+    int (*CommDestroy)(nccl_comm);
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t);
+    int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t);
+    int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    const char *(*GetErrorString)(int);
+} N;
+
+static int nccl_load()
+{
+    if (N.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !N.lib; ++i) N.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!N.lib) return dkb_fail(DKB_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(f)                                                                 \
+    *(void **)(&N.f) = dlsym(N.lib, "nccl" #f);                                \
+    if (!N.f) return dkb_fail(DKB_E_NCCL, "libnccl lacks nccl" #f)
+    SYM(GetUniqueId);
+    SYM(CommInitRank);
+    SYM(CommDestroy);
+    SYM(AllReduce);
+    SYM(Send);
+    SYM(Recv);
+    SYM(GroupStart);
+    SYM(GroupEnd);
+    SYM(GetErrorString);
+#undef SYM
+    return 0;
+}
+static void nccl_check(int r, const char *what)
+{
+    if (r != 0) {
+        fprintf(stderr, "daskr_b200: NCCL error in %s: %s\n", what, N.GetErrorString ? N.GetErrorString(r) : "?");
+        abort();
+    }
+}
+
+void allreduce_sum(int slot, int count)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return;
+    nccl_check(N.AllReduce(c->d_scal + slot, c->d_scal + slot, count, NCCL_F64, NCCL_SUM, c->comm, c->stream), "allreduce_sum");
+}
+void allreduce_max(int slot, int count)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return;
+    nccl_check(N.AllReduce(c->d_scal + slot, c->d_scal + slot, count, NCCL_F64, NCCL_MAX, c->comm, c->stream), "allreduce_max");
+}
+void allreduce_min_int(int *d_val, int count)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return;
+    nccl_check(N.AllReduce(d_val, d_val, count, NCCL_INT32, NCCL_MIN, c->comm, c->stream), "allreduce_min_int");
+}
+
+// K9: one mesh row to each slab neighbour (ghost row of the lower neighbour's top, and v.v.)
+static void halo_exchange_n(double *const *vecs, int nv)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return;
+    ProfScope ps(PROF_HALO);
+    const i64 h = c->halo, n = c->neq;
+    nccl_check(N.GroupStart(), "halo group");
+    for (int k = 0; k < nv; ++k) {
+        double *v = vecs[k];
+        if (c->rank > 0) {
+            nccl_check(N.Send(v, h, NCCL_F64, c->rank - 1, c->comm, c->stream), "halo send lo");
+            nccl_check(N.Recv(v - h, h, NCCL_F64, c->rank - 1, c->comm, c->stream), "halo recv lo");
+        }
+        if (c->rank < c->nranks - 1) {
+            nccl_check(N.Send(v + n - h, h, NCCL_F64, c->rank + 1, c->comm, c->stream), "halo send hi");
+            nccl_check(N.Recv(v + n, h, NCCL_F64, c->rank + 1, c->comm, c->stream), "halo recv hi");
+        }
+    }
+    nccl_check(N.GroupEnd(), "halo group");
+}
+void halo_exchange(double *vec) { halo_exchange_n(&vec, 1); }
+void halo_exchange3(double *a, double *b, double *cc)
+{
+    double *v[3] = {a, b, cc};
+    halo_exchange_n(v, 3);
+}
+
+// ---------------------------------------------------------------- profiling
+static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo"};
+void prof_begin(int slot)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->prof_on) return;
+    if (c->ev_slot.size() >= 200000) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+    c->ev_pool.push_back(a);
+    c->ev_pool.push_back(b);
+    c->ev_slot.push_back(slot);
+}
+void prof_end(int slot)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->prof_on) return;
+    // the matching begin is the last open pair of this slot
+    for (i64 i = (i64)c->ev_slot.size() - 1; i >= 0; --i)
+        if (c->ev_slot[i] == slot) {
+            cudaEventRecord(c->ev_pool[2 * i + 1], c->stream);
+            c->ev_slot[i] = slot + 1000;   // closed
+            return;
+        }
+}
+static void prof_collect()
+{
+    DkbCtx *c = g_ctx;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->ev_slot.size(); ++i) {
+        int s = c->ev_slot[i];
+        if (s >= 1000) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]) == cudaSuccess) {
+                c->prof[s - 1000].ms += ms;
+                c->prof[s - 1000].launches += 1;
+            }
+        }
+        cudaEventDestroy(c->ev_pool[2 * i]);
+        cudaEventDestroy(c->ev_pool[2 * i + 1]);
+    }
+    c->ev_pool.clear();
+    c->ev_slot.clear();
+    cudaGetLastError();
+}
+
+extern "C" {
+
+int dkb_version(void) { return DKB_VERSION; }
+const char *dkb_last_error(void) { return g_err; }
+
+int dkb_init(int device)
+{
+    if (g_ctx) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return dkb_fail(DKB_E_CUDA, "no CUDA device visible (%s); daskr_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return dkb_fail(DKB_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    DkbCtx *c = new DkbCtx();
+    c->device = device;
+    g_ctx = c;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_scal, sizeof(double) * DKB_NSLOT));
+    CUDA_TRY(cudaMemset(c->d_scal, 0, sizeof(double) * DKB_NSLOT));
+    CUDA_TRY(cudaMallocHost(&c->h_scal, sizeof(double) * DKB_NSLOT));
+    CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * DKB_RED_MAXGRID * 8));
+    CUDA_TRY(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(c->d_ticket, 0, sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&c->d_iflag, sizeof(int) * 4));
+    CUDA_TRY(cudaMallocHost(&c->h_iflag, sizeof(int) * 4));
+    for (int i = 0; i < PROF_NSLOTS; ++i) {
+        memset(&c->prof[i], 0, sizeof(ProfSlot));
+        strncpy(c->prof[i].name, prof_names[i], sizeof(c->prof[i].name) - 1);
+    }
+    return 0;
+}
+
+int dkb_finalize(void)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return 0;
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && N.CommDestroy) N.CommDestroy(c->comm);
+    cudaFree(c->arena);
+    cudaFree(c->wp);
+    cudaFree(c->iwp);
+    cudaFree(c->d_id);
+    cudaFree(c->d_icnstr);
+    cudaFree(c->d_rtol);
+    cudaFree(c->d_atol);
+    cudaFree(c->d_sx);
+    cudaFree(c->d_scal);
+    cudaFree(c->d_part);
+    cudaFree(c->d_ticket);
+    cudaFree(c->d_iflag);
+    cudaFreeHost(c->h_scal);
+    cudaFreeHost(c->h_iflag);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    g_ctx = nullptr;
+    return 0;
+}
+
+void *dkb_stream(void) { return g_ctx ? (void *)g_ctx->stream : nullptr; }
+
+int dkb_sync(void)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaStreamSynchronize(g_ctx->stream));
+    return 0;
+}
+
+int dkb_set_option(int opt, int64_t value)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    switch (opt) {
+    case DKB_OPT_DEVICE_IO: g_ctx->opt_device_io = value != 0; break;
+    case DKB_OPT_FUSED: g_ctx->opt_fused = value != 0; break;
+    case DKB_OPT_MAX_STEPS: g_ctx->opt_max_steps = value > 0 ? value : 500; break;
+    default: return dkb_fail(DKB_E_ARG, "unknown option %d", opt);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- communicator
+int dkb_comm_unique_id(void *id128)
+{
+    int r = nccl_load();
+    if (r) return r;
+    nccl_uid id;
+    if (N.GetUniqueId(&id) != 0) return dkb_fail(DKB_E_NCCL, "ncclGetUniqueId failed");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int dkb_comm_init(const void *id128, int rank, int nranks)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (nranks <= 1) {
+        c->rank = 0;
+        c->nranks = 1;
+        return 0;
+    }
+    int r = nccl_load();
+    if (r) return r;
+    nccl_uid id;
+    memcpy(&id, id128, 128);
+    nccl_comm comm;
+    int e = N.CommInitRank(&comm, nranks, id, rank);
+    if (e != 0) return dkb_fail(DKB_E_NCCL, "ncclCommInitRank: %s", N.GetErrorString(e));
+    c->comm = comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    return 0;
+}
+
+// ---------------------------------------------------------------- setup_rbdpre (DMSET2)
+// src/daskr_rbdpre.f90:102-156.  The mesh rows are split evenly over the ranks (y-slabs).
+void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *nsd, const int *lid, int *iwork)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) {
+        fprintf(stderr, "daskr_b200: dkb_setup_rbdpre called before dkb_init\n");
+        abort();
+    }
+    c->mx = *mx;
+    c->my_g = *my;
+    c->ns = *ns;
+    c->nsd = *nsd;
+    const int base = c->my_g / c->nranks, rem = c->my_g % c->nranks;
+    c->my = base + (c->rank < rem ? 1 : 0);
+    c->jy0 = c->rank * base + std::min(c->rank, rem);
+    c->npts = (i64)c->mx * c->my;
+    c->halo = (i64)c->ns * c->mx;
+    c->halo_pad = ((c->halo + 31) / 32) * 32;
+    c->rbd_set = 1;
+    // blocks and pivots are device resident and sized in 64 bits: nothing is carved from rwork/iwork
+    int *IW = iwork - 1;
+    IW[27] = 0;
+    IW[28] = 0;
+    if (*lid == 0) return;
+    i64 i0 = *lid;
+    for (int jy = 1; jy <= c->my; ++jy)
+        for (int jx = 1; jx <= c->mx; ++jx) {
+            for (int i = 1; i <= c->nsd; ++i) IW[i0 + i] = 1;
+            for (int i = c->nsd + 1; i <= c->ns; ++i) IW[i0 + i] = -1;
+            i0 = i0 + c->ns;
+        }
+}
+
+int dkb_slab(int *jy0, int *myloc)
+{
+    if (!g_ctx || !g_ctx->rbd_set) return dkb_fail(DKB_E_STATE, "dkb_setup_rbdpre not called");
+    *jy0 = g_ctx->jy0;
+    *myloc = g_ctx->my;
+    return 0;
+}
+
+// ---------------------------------------------------------------- food web
+// setpar, example/example_web.f90:19-58
+int dkb_web_setpar(int np, int mx, int my)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (2 * np > DKB_NS_MAX || np < 1) return dkb_fail(DKB_E_ARG, "np=%d: ns=2*np must be in 2..%d", np, DKB_NS_MAX);
+    if (!c->rbd_set || c->mx != mx || c->my_g != my || c->ns != 2 * np)
+        return dkb_fail(DKB_E_STATE, "call dkb_setup_rbdpre(mx,my,ns=2*np,...) with the same mesh first");
+    WebPar &w = c->web;
+    memset(&w, 0, sizeof(w));
+    w.np = np;
+    w.ns = 2 * np;
+    w.mx = mx;
+    w.my = my;
+    w.ax = 1.0;
+    w.ay = 1.0;
+    w.aa = 1.0;
+    w.ee = 1e4;
+    w.gg = 0.5e-6;
+    w.bb = 1.0;
+    w.dprey = 1.0;
+    w.dpred = 0.05;
+    w.alpha = 5e1;
+    w.beta = 3e2;
+    w.dx = w.ax / (mx - 1);
+    w.dy = w.ay / (my - 1);
+    const int ns = w.ns;
+#define ACOEF(i, j) w.acoef[((j) - 1) * ns + ((i) - 1)]
+    for (int j = 1; j <= np; ++j) {
+        for (int i = 1; i <= np; ++i) {
+            ACOEF(np + i, j) = w.ee;
+            ACOEF(i, np + j) = -w.gg;
+        }
+        ACOEF(j, j) = -w.aa;
+        ACOEF(np + j, np + j) = -w.aa;
+        w.bcoef[j - 1] = w.bb;
+        w.bcoef[np + j - 1] = -w.bb;
+    }
+#undef ACOEF
+    for (int i = 1; i <= ns; ++i) {
+        const double diff = (i <= np) ? w.dprey : w.dpred;
+        w.cox[i - 1] = diff / (w.dx * w.dx);
+        w.coy[i - 1] = diff / (w.dy * w.dy);
+    }
+    c->problem = DKB_PROB_WEB;
+    web_upload_tables();
+    return 0;
+}
+
+// cinit, example/example_web.f90:102-148, for this rank's rows (host arrays).  The prey rates
+// cdot = f(c) need the mesh neighbours, so the full rows jy0-1 .. jy0+my are generated locally
+// (the initial profile is a closed-form function of x and y).
+int dkb_web_cinit(double *cout, double *cdotout, double pred_ic)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || c->problem != DKB_PROB_WEB) return dkb_fail(DKB_E_STATE, "dkb_web_setpar not called");
+    const WebPar &w = c->web;
+    const int ns = w.ns, np = w.np, mx = w.mx, myg = w.my;
+    const i64 mxns = (i64)mx * ns;
+    const double pi = 4 * atan(1.0);
+    auto cval = [&](int jy /*global, 1-based*/, int jx, int i) -> double {
+        if (i > np) return pred_ic;
+        double y = (jy - 1) * w.dy;
+        double argy = 16 * y * y * (w.ay - y) * (w.ay - y);
+        double x = (jx - 1) * w.dx;
+        double argx = 16 * x * x * (w.ax - x) * (w.ax - x);
+        return 10.0 + i * argx * argy;
+    };
+    std::vector<double> rxy(ns), cpt(ns);
+    for (int jl = 1; jl <= c->my; ++jl) {
+        const int jy = c->jy0 + jl;
+        const int jyu = (jy == myg) ? jy - 1 : jy + 1, jyl = (jy == 1) ? jy + 1 : jy - 1;
+        const double y = (jy - 1) * w.dy;
+        for (int jx = 1; jx <= mx; ++jx) {
+            const int jxu = (jx == mx) ? jx - 1 : jx + 1, jxl = (jx == 1) ? jx + 1 : jx - 1;
+            const double x = (jx - 1) * w.dx;
+            const double fac = 1.0 + w.alpha * x * y + w.beta * sin(4 * pi * x) * sin(4 * pi * y);
+            for (int i = 1; i <= ns; ++i) cpt[i - 1] = cval(jy, jx, i);
+            for (int k = 0; k < ns; ++k) rxy[k] = 0.0;
+            for (int i = 1; i <= ns; ++i)
+                for (int k = 1; k <= ns; ++k) rxy[k - 1] = rxy[k - 1] + cpt[i - 1] * w.acoef[(i - 1) * ns + (k - 1)];
+            for (int i = 0; i < ns; ++i) rxy[i] = cpt[i] * (w.bcoef[i] * fac + rxy[i]);
+            const i64 ioff = mxns * (jl - 1) + (i64)ns * (jx - 1);
+            for (int i = 1; i <= ns; ++i) {
+                const double ci = cpt[i - 1];
+                cout[ioff + i - 1] = ci;
+                if (i > np) {
+                    cdotout[ioff + i - 1] = 0.0;
+                } else {
+                    const double dcyli = ci - cval(jyl, jx, i), dcyui = cval(jyu, jx, i) - ci;
+                    const double dcxli = ci - cval(jy, jxl, i), dcxui = cval(jy, jxu, i) - ci;
+                    cdotout[ioff + i - 1] = w.coy[i - 1] * (dcyui - dcyli) + w.cox[i - 1] * (dcxui - dcxli) + rxy[i - 1];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+static void require_problem(int prob, const char *who)
+{
+    if (!g_ctx || g_ctx->problem != prob) {
+        fprintf(stderr, "daskr_b200: %s called without its problem set up (dkb_init / dkb_setup_rbdpre / setpar)\n", who);
+        abort();
+    }
+}
+
+// res, example/example_web.f90:190-224
+void dkb_web_res(const double *t, const double *cc, const double *cdot, const double *cj, double *delta, int *ires,
+                 double *rpar, int *ipar)
+{
+    (void)t; (void)cj; (void)ires; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_WEB, "dkb_web_res");
+    if (g_ctx->nranks > 1) halo_exchange(const_cast<double *>(cc));
+    web_res_launch(cc, cdot, delta);
+}
+
+static int fetch_first_flag(DkbCtx *c)
+{
+    allreduce_min_int(c->d_iflag + 1, 1);
+    cudaMemcpyAsync(c->h_iflag + 1, c->d_iflag + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    dkb_cuda_check("jac");
+    return c->h_iflag[1] == INT_MAX ? 0 : c->h_iflag[1];
+}
+static void arm_first_flag(DkbCtx *c)
+{
+    c->h_iflag[1] = INT_MAX;
+    cudaMemcpyAsync(c->d_iflag + 1, c->h_iflag + 1, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+}
+
+// jac, example/example_web.f90:301-344 -> jac_rbdpre (R0 is recomputed in the kernel, which the
+// reference sanctions at daskr_rbdpre.f90:215-218; it equals the rpar copy the reference reads)
+void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *cc, double *cdot,
+                 const double *rewt, double *savr, double *wk, const double *h, const double *cj, double *rwp,
+                 int *iwp, int *ierr, double *rpar, int *ipar)
+{
+    (void)res; (void)ires; (void)neq; (void)t; (void)cdot; (void)savr; (void)wk; (void)h; (void)rpar;
+    require_problem(DKB_PROB_WEB, "dkb_web_jac");
+    DkbCtx *c = g_ctx;
+    if (ipar && ipar[1] != 0) {
+        fprintf(stderr, "daskr_b200: block-grouping (jbg=1) is not implemented\n");
+        *ierr = -1;
+        return;
+    }
+    arm_first_flag(c);
+    web_jac_launch(cc, rewt, *cj, rwp, iwp, c->d_iflag + 1);
+    // ierr = dgefa info of the first failing block in the reference; here its block number
+    *ierr = fetch_first_flag(c);
+}
+
+// psol, example/example_web.f90:346-391 with jpre = 1
+void dkb_web_psol(const int *neq, const double *t, const double *cc, const double *cdot, const double *savr,
+                  double *wk, const double *cj, const double *wght, double *rwp, int *iwp, double *b,
+                  const double *epslin, int *ierr, double *rpar, int *ipar)
+{
+    (void)neq; (void)t; (void)cc; (void)cdot; (void)savr; (void)wk; (void)cj; (void)wght; (void)epslin; (void)rpar;
+    require_problem(DKB_PROB_WEB, "dkb_web_psol");
+    *ierr = 0;
+    if (ipar && (ipar[0] != 1 || ipar[1] != 0)) {
+        fprintf(stderr, "daskr_b200: only jpre=1 (reaction factor), jbg=0 is implemented on device\n");
+        *ierr = -1;
+        return;
+    }
+    lu_dgesl_batched(rwp, iwp, g_ctx->ns, g_ctx->npts, b);
+}
+
+void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd)
+{
+    if (!g_ctx || !g_ctx->rbd_set) {
+        fprintf(stderr, "daskr_b200: dkb_psol_rbdpre before dkb_setup_rbdpre\n");
+        abort();
+    }
+    lu_dgesl_batched(bd, ipbd, g_ctx->ns, g_ctx->npts, b);
+}
+
+// ---------------------------------------------------------------- heat
+int dkb_heat_setpar(int m)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (!c->rbd_set || c->mx != m + 2 || c->my_g != m + 2 || c->ns != 1)
+        return dkb_fail(DKB_E_STATE, "call dkb_setup_rbdpre(m+2, m+2, 1, 1, 0, iwork) first");
+    c->heat.m = m;
+    c->heat.dx = 1.0 / (m + 1);
+    c->heat.coeff = 1.0 / (c->heat.dx * c->heat.dx);
+    c->problem = DKB_PROB_HEAT;
+    return 0;
+}
+
+// uinit, example/example_heat.f90:19-51 (this rank's rows)
+int dkb_heat_uinit(double *u, double *udot)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || c->problem != DKB_PROB_HEAT) return dkb_fail(DKB_E_STATE, "dkb_heat_setpar not called");
+    const int m = c->heat.m;
+    const double dx = c->heat.dx;
+    for (int kl = 0; kl < c->my; ++kl) {
+        const int k = c->jy0 + kl;
+        const double yk = k * dx;
+        const i64 ioff = (i64)(m + 2) * kl;
+        for (int j = 0; j <= m + 1; ++j) {
+            const double xj = j * dx;
+            u[ioff + j] = 16 * xj * (1.0 - xj) * yk * (1.0 - yk);
+            udot[ioff + j] = 0.0;
+        }
+    }
+    return 0;
+}
+
+void dkb_heat_res(const double *t, const double *u, const double *udot, const double *cj, double *delta, int *ires,
+                  double *rpar, int *ipar)
+{
+    (void)t; (void)cj; (void)ires; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_HEAT, "dkb_heat_res");
+    if (g_ctx->nranks > 1) halo_exchange(const_cast<double *>(u));
+    heat_res_launch(u, udot, delta);
+}
+
+void dkb_heat_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *u, double *udot,
+                  const double *rewt, double *savr, double *wk, const double *h, const double *cj, double *rwp,
+                  int *iwp, int *ierr, double *rpar, int *ipar)
+{
+    (void)res; (void)ires; (void)neq; (void)t; (void)udot; (void)savr; (void)wk; (void)h; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_HEAT, "dkb_heat_jac");
+    DkbCtx *c = g_ctx;
+    arm_first_flag(c);
+    heat_jac_launch(u, rewt, *cj, rwp, iwp, c->d_iflag + 1);
+    *ierr = fetch_first_flag(c);
+}
+
+void dkb_heat_psol(const int *neq, const double *t, const double *u, const double *udot, const double *savr,
+                   double *wk, const double *cj, const double *wght, double *rwp, int *iwp, double *b,
+                   const double *epslin, int *ierr, double *rpar, int *ipar)
+{
+    (void)neq; (void)t; (void)u; (void)udot; (void)savr; (void)wk; (void)cj; (void)wght; (void)epslin; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_HEAT, "dkb_heat_psol");
+    *ierr = 0;
+    lu_dgesl_batched(rwp, iwp, 1, g_ctx->npts, b);
+}
+
+// ---------------------------------------------------------------- hot path as separate calls
+void dkb_dslvk(const int *neq, const double *y, const double *t, const double *ydot, const double *savr, double *x,
+               double *ewt, int *iwm, dkb_res_t res, int *ires, dkb_psol_t psol, int *iersl, const double *cj,
+               const double *epslin, const double *sqrtn, const double *rsqrtn, double *rhok, double *rpar, int *ipar)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena || c->neq != *neq) {
+        fprintf(stderr, "daskr_b200: dkb_dslvk needs the solver workspace of a dkb_daskr initial call with the same neq\n");
+        *iersl = -1;
+        *ires = 0;
+        return;
+    }
+    k_dslvk(*neq, y, *t, ydot, savr, x, ewt, iwm, res, ires, psol, iersl, *cj, *epslin, *sqrtn, *rsqrtn, rhok, rpar,
+            ipar);
+}
+
+double dkb_ddwnrm(const int *neq, const double *v, const double *rwt)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) {
+        fprintf(stderr, "daskr_b200: dkb_ddwnrm before dkb_init\n");
+        abort();
+    }
+    const i64 save = c->neq_g;
+    if (c->nranks <= 1) c->neq_g = *neq;
+    double r = r_wrms(*neq, v, rwt);
+    c->neq_g = save;
+    return r;
+}
+
+// ---------------------------------------------------------------- batched LINPACK micro-API
+int dkb_dgefa_batched(double *bd, int *ipbd, int ns, int64_t nblk, int *info, int64_t *info_first)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (ns < 1 || ns > DKB_NS_MAX) return dkb_fail(DKB_E_ARG, "ns=%d out of range 1..%d", ns, DKB_NS_MAX);
+    if (nblk > 2147483645) return dkb_fail(DKB_E_ARG, "nblk too large for the int32 first-failure flag");
+    c->h_iflag[2] = INT_MAX;
+    CUDA_TRY(cudaMemcpyAsync(c->d_iflag + 2, c->h_iflag + 2, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    int r = lu_dgefa_batched(bd, ipbd, ns, nblk, info, c->d_iflag + 2);
+    if (r) return r;
+    CUDA_TRY(cudaMemcpyAsync(c->h_iflag + 2, c->d_iflag + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    if (info_first) *info_first = (c->h_iflag[2] == INT_MAX) ? 0 : c->h_iflag[2];
+    return 0;
+}
+
+int dkb_dgesl_batched(const double *bd, const int *ipbd, int ns, int64_t nblk, double *b)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (ns < 1 || ns > DKB_NS_MAX) return dkb_fail(DKB_E_ARG, "ns=%d out of range 1..%d", ns, DKB_NS_MAX);
+    int r = lu_dgesl_batched(bd, ipbd, ns, nblk, b);
+    if (r) return r;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- memory helpers
+int dkb_malloc(void **ptr, int64_t bytes)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+    return 0;
+}
+int dkb_free(void *ptr)
+{
+    CUDA_TRY(cudaFree(ptr));
+    return 0;
+}
+int dkb_memcpy_h2d(void *dst, const void *src, int64_t bytes)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, g_ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx->stream));
+    return 0;
+}
+int dkb_memcpy_d2h(void *dst, const void *src, int64_t bytes)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, g_ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx->stream));
+    return 0;
+}
+int dkb_memset(void *dst, int value, int64_t bytes)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaMemsetAsync(dst, value, (size_t)bytes, g_ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- measurement hooks
+int dkb_prof_enable(int on)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (!on && g_ctx->prof_on) prof_collect();
+    g_ctx->prof_on = on != 0;
+    return 0;
+}
+int dkb_prof_reset(void)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    prof_collect();
+    for (int i = 0; i < PROF_NSLOTS; ++i) {
+        g_ctx->prof[i].ms = 0.0;
+        g_ctx->prof[i].launches = 0;
+    }
+    g_ctx->launches = 0;
+    return 0;
+}
+int dkb_prof_get(char *names, double *ms, int64_t *launches, int max_entries)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    prof_collect();
+    int n = std::min<int>(PROF_NSLOTS, max_entries);
+    for (int i = 0; i < n; ++i) {
+        strncpy(names + 48 * i, g_ctx->prof[i].name, 47);
+        names[48 * i + 47] = 0;
+        ms[i] = g_ctx->prof[i].ms;
+        launches[i] = g_ctx->prof[i].launches;
+    }
+    return n;
+}
+int64_t dkb_launch_count(void) { return g_ctx ? g_ctx->launches : 0; }
+
+} // extern "C"

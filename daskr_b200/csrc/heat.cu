@@ -1,0 +1,142 @@
+// heat.cu -- device kernels of the 2-D heat problem (example/example_heat.f90:53-89)
+// with the reaction-based block-diagonal preconditioner at ns = nsd = 1.
+//
+// The reference pairs this problem with the banded preconditioner; BASELINE
+// config 3 asks for rbdpre, which is not shipped, so the rblock routine is the
+// one SURVEY.md 8(d) defines (and the oracle restates identically):
+//   R = -4*coeff*u on interior points,  R = (cj-1)*u on boundary points,
+// so that each 1x1 block cj - dR/du is the true Jacobian diagonal.
+// One thread per mesh point; (m+2)^2 mesh, row-major by y, slab-decomposed rows.
+#include "dkb_internal.h"
+
+struct HeatDev {
+    int m2, my, jy0, my_g;
+    double coeff, srur, cj;
+};
+static HeatDev make_heatdev(double cj)
+{
+    DkbCtx *c = g_ctx;
+    HeatDev h;
+    h.m2 = c->heat.m + 2;
+    h.my = c->my;
+    h.jy0 = c->jy0;
+    h.my_g = c->my_g;
+    h.coeff = c->heat.coeff;
+    h.srur = 1.4901161193847656e-08;
+    h.cj = cj;
+    return h;
+}
+
+__device__ __forceinline__ bool heat_interior(const HeatDev &h, i64 i)
+{
+    const int k = (int)(i / h.m2) + h.jy0;
+    const int j = (int)(i % h.m2);
+    return j >= 1 && j <= h.m2 - 2 && k >= 1 && k <= h.my_g - 2;
+}
+
+// res:72-87: delta = u everywhere, then interior delta = udot - (temx + temy - 4u)*coeff
+template <class State>
+__device__ __forceinline__ double heat_point_res(const HeatDev &h, const State &S, i64 i, double ui, double udot_i)
+{
+    if (!heat_interior(h, i)) return ui;
+    const double temx = S(i - 1) + S(i + 1);
+    const double temy = S(i - h.m2) + S(i + h.m2);
+    return udot_i - (temx + temy - 4 * ui) * h.coeff;
+}
+
+struct HStatePlain {
+    const double *u;
+    __device__ __forceinline__ double operator()(i64 i) const { return __ldg(u + i); }
+};
+struct HStateDatv {
+    const double *y, *v, *wt;
+    double wscale;
+    __device__ __forceinline__ double operator()(i64 i) const
+    {
+        return __ldg(y + i) + __ldg(v + i) / (wscale * __ldg(wt + i));
+    }
+};
+
+__global__ void __launch_bounds__(256) heat_res_kernel(HeatDev h, i64 n, const double *__restrict__ u,
+                                                       const double *__restrict__ udot, double *__restrict__ delta)
+{
+    HStatePlain S{u};
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        delta[i] = heat_point_res(h, S, i, S(i), __ldg(udot + i));
+}
+
+__device__ __forceinline__ double heat_rblock(const HeatDev &h, i64 i, double u)
+{
+    return heat_interior(h, i) ? (-4 * h.coeff * u) : ((h.cj - 1.0) * u);
+}
+
+// jac_rbdpre (src/daskr_rbdpre.f90:209-249) at ns = 1, dgefa of a 1x1 block (info = 1 if zero)
+__global__ void __launch_bounds__(256) heat_jac_kernel(HeatDev h, i64 n, const double *__restrict__ u,
+                                                       const double *__restrict__ rewt, double *__restrict__ bd,
+                                                       int *__restrict__ ipbd, int *first_flag)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double uj = u[i];
+        const double r0 = heat_rblock(h, i, uj);
+        const double del = fmax(h.srur * fabs(uj), 1e-2 / rewt[i]);
+        const double fac = -1.0 / del;
+        const double r1 = heat_rblock(h, i, uj + del);
+        double b = (r1 - r0) * fac;
+        b = b + h.cj;
+        bd[i] = b;
+        ipbd[i] = 1;
+        if (b == 0.0) atomicMin(first_flag, (int)(i < 2147483646 ? i + 1 : 2147483646));
+    }
+}
+
+// fused datv (src/daskr_new.f90:3493-3518) with res and the 1x1 dgesl inlined
+__global__ void __launch_bounds__(256) heat_datv_kernel(HeatDev h, i64 n, const double *__restrict__ v,
+                                                        const double *__restrict__ wt, double wscale,
+                                                        const double *__restrict__ y, const double *__restrict__ ydot,
+                                                        const double *__restrict__ savr, double cj,
+                                                        const double *__restrict__ bd, double *__restrict__ vnext)
+{
+    HStateDatv S{y, v, wt, wscale};
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double wgt = wscale * __ldg(wt + i);
+        const double vtmp = __ldg(v + i) / wgt;
+        const double zi = __ldg(y + i) + vtmp;
+        const double ydt = __ldg(ydot + i) + vtmp * cj;
+        double d = heat_point_res(h, S, i, zi, ydt);
+        d = d - __ldg(savr + i);
+        d = d / __ldg(bd + i);
+        vnext[i] = d * wgt;
+    }
+}
+
+static int hgrid(i64 n)
+{
+    i64 g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+void heat_res_launch(const double *u, const double *udot, double *delta)
+{
+    DkbCtx *c = g_ctx;
+    heat_res_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(0.0), c->npts, u, udot, delta);
+    COUNT_LAUNCH();
+}
+void heat_jac_launch(const double *u, const double *rewt, double cj, double *bd, int *ipbd, int *d_first_flag)
+{
+    DkbCtx *c = g_ctx;
+    heat_jac_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, u, rewt, bd, ipbd, d_first_flag);
+    COUNT_LAUNCH();
+}
+void heat_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+                     const double *savr, double cj, const double *bd, double *vnext)
+{
+    DkbCtx *c = g_ctx;
+    heat_datv_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, v, wt, wscale, y, ydot,
+                                                            savr, cj, bd, vnext);
+    COUNT_LAUNCH();
+}

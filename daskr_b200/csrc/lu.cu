@@ -1,0 +1,196 @@
+// lu.cu -- batched LINPACK dgefa / dgesl for the ns x ns reaction blocks
+// (K5/K6 of SURVEY.md 2.3; src/linpack.f90:325-431, 433-520).
+//
+// Layout is the reference's (src/daskr_rbdpre.f90:237-249): block p at
+// bd + p*ns*ns, column-major; pivots 1-based int32 at ipbd + p*ns.
+// One sub-warp group of G = 2^ceil(log2 ns) lanes owns one block; lane i holds
+// ROW i of the block in registers (a[j] = A(i,j)), so a column is one coalesced
+// ns*8-byte segment per load and every elimination / substitution step is a
+// width-G shuffle broadcast plus one multiply-add per lane.  Arithmetic is the
+// reference's operation for operation (negated multipliers, first-max pivot,
+// separate multiply and add via -fmad=false), which is what makes the pivot
+// indices bit-identical to the CPU path.
+#include "dkb_internal.h"
+
+#include "lu_device.cuh"
+
+// ------------------------------------------------------------------ kernels
+template <int NS>
+__global__ void __launch_bounds__(256) dgefa_kernel(double *bd, int *ipbd, i64 nblk, int *info, int *first_flag)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const int li = threadIdx.x % G;
+    const i64 gpb = blockDim.x / G;
+    const i64 ngroups = (i64)gridDim.x * gpb;
+    const i64 nloop = (nblk + ngroups - 1) / ngroups;   // uniform trip count: shuffles need whole groups
+    for (i64 it = 0; it < nloop; ++it) {
+        i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
+        const bool live = p < nblk;
+        if (!live) p = nblk - 1;
+        double *blk = bd + p * (NS * NS);
+        double a[NS];
+        group_load_block<NS>(blk, li, a);
+        int ipv;
+        int inf = group_dgefa<NS>(a, li, ipv);
+        if (live && li < NS) {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) blk[j * NS + li] = a[j];
+            ipbd[p * NS + li] = ipv;
+            if (li == 0) {
+                if (info) info[p] = inf;
+                if (inf != 0 && first_flag) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
+            }
+        }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) dgesl_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
+                                                    i64 nblk, double *b)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const int li = threadIdx.x % G;
+    const i64 gpb = blockDim.x / G;
+    const i64 ngroups = (i64)gridDim.x * gpb;
+    const i64 nloop = (nblk + ngroups - 1) / ngroups;
+    for (i64 it = 0; it < nloop; ++it) {
+        i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
+        const bool live = p < nblk;
+        if (!live) p = nblk - 1;
+        double a[NS];
+        group_load_block<NS>(bd + p * (NS * NS), li, a);
+        int ipv = (li < NS) ? __ldg(ipbd + p * NS + li) : 1;
+        double bi = (li < NS) ? b[p * NS + li] : 0.0;
+        bi = group_dgesl<NS>(a, ipv, li, bi);
+        if (live && li < NS) b[p * NS + li] = bi;
+    }
+}
+
+// dspigm prologue (:3277-3289): out = (wscale*wt) * P^-1 in, plus sum of squares of out
+template <int NS>
+__global__ void __launch_bounds__(256) psol_scaled_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
+                                                          i64 nblk, const double *__restrict__ in,
+                                                          const double *__restrict__ wt, double wscale,
+                                                          double *out, double *part, unsigned *ticket, double *res)
+{
+    constexpr int G = GroupOf<NS>::G;
+    __shared__ double sh[8];
+    __shared__ int is_last;
+    const int li = threadIdx.x % G;
+    const i64 gpb = blockDim.x / G;
+    const i64 ngroups = (i64)gridDim.x * gpb;
+    const i64 nloop = (nblk + ngroups - 1) / ngroups;
+    double acc = 0.0;
+    for (i64 it = 0; it < nloop; ++it) {
+        i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
+        const bool live = p < nblk;
+        if (!live) p = nblk - 1;
+        double a[NS];
+        group_load_block<NS>(bd + p * (NS * NS), li, a);
+        int ipv = (li < NS) ? __ldg(ipbd + p * NS + li) : 1;
+        double bi = (li < NS) ? in[p * NS + li] : 0.0;
+        bi = group_dgesl<NS>(a, ipv, li, bi);
+        if (live && li < NS) {
+            double w = wscale * wt[p * NS + li];
+            double o = bi * w;
+            out[p * NS + li] = o;
+            acc = acc + o * o;
+        }
+    }
+    // block reduction + last-block final stage (same scheme as vecops.cu)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) sh[wid] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+        part[(i64)blockIdx.x * 8] = s;
+        __threadfence();
+        unsigned t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) s += __ldcg(&part[(i64)b * 8]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if (lane == 0) sh[wid] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+            res[0] = tot;
+        }
+    }
+}
+
+static int lu_grid(i64 nblk, int G)
+{
+    i64 gpb = 256 / G;
+    i64 g = (nblk + gpb - 1) / gpb;
+    i64 cap = 148 * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+#define NS_DISPATCH(ns, CALL)                                                                   \
+    switch (ns) {                                                                               \
+    case 1: { CALL(1); } break;                                                                 \
+    case 2: { CALL(2); } break;                                                                 \
+    case 3: { CALL(3); } break;                                                                 \
+    case 4: { CALL(4); } break;                                                                 \
+    case 5: { CALL(5); } break;                                                                 \
+    case 6: { CALL(6); } break;                                                                 \
+    case 8: { CALL(8); } break;                                                                 \
+    case 10: { CALL(10); } break;                                                               \
+    case 12: { CALL(12); } break;                                                               \
+    case 16: { CALL(16); } break;                                                               \
+    case 20: { CALL(20); } break;                                                               \
+    case 24: { CALL(24); } break;                                                               \
+    case 32: { CALL(32); } break;                                                               \
+    default: return dkb_fail(DKB_E_UNSUPPORTED, "block size ns=%d not instantiated (1-6,8,10,12,16,20,24,32)", ns); \
+    }
+
+int lu_dgefa_batched(double *bd, int *ipbd, int ns, i64 nblk, int *info, int *d_first_flag)
+{
+    if (nblk <= 0) return 0;
+    cudaStream_t st = g_ctx->stream;
+#define CALL(N) dgefa_kernel<N><<<lu_grid(nblk, GroupOf<N>::G), 256, 0, st>>>(bd, ipbd, nblk, info, d_first_flag)
+    NS_DISPATCH(ns, CALL)
+#undef CALL
+    COUNT_LAUNCH();
+    return 0;
+}
+
+int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double *b)
+{
+    if (nblk <= 0) return 0;
+    cudaStream_t st = g_ctx->stream;
+#define CALL(N) dgesl_kernel<N><<<lu_grid(nblk, GroupOf<N>::G), 256, 0, st>>>(bd, ipbd, nblk, b)
+    NS_DISPATCH(ns, CALL)
+#undef CALL
+    COUNT_LAUNCH();
+    return 0;
+}
+
+int lu_psol_scaled(const double *bd, const int *ipbd, int ns, i64 nblk, const double *in, const double *wt,
+                   double wscale, double *out, int slot)
+{
+    DkbCtx *c = g_ctx;
+    if (nblk <= 0) return 0;
+    cudaStream_t st = c->stream;
+#define CALL(N)                                                                                                   \
+    psol_scaled_kernel<N><<<lu_grid(nblk, GroupOf<N>::G), 256, 0, st>>>(bd, ipbd, nblk, in, wt, wscale, out,    \
+                                                                        c->d_part, c->d_ticket, c->d_scal + slot)
+    NS_DISPATCH(ns, CALL)
+#undef CALL
+    COUNT_LAUNCH();
+    allreduce_sum(slot, 1);
+    return 0;
+}

@@ -1,0 +1,105 @@
+// lu_device.cuh -- in-register LINPACK dgefa / dgesl for one ns x ns block per sub-warp group.
+// Shared by lu.cu (batched micro-API, psol) and the problem kernels (web.cu, heat.cu) that
+// fuse the block solve into the residual sweep.  See lu.cu for the layout and the mapping.
+#pragma once
+#include "dkb_internal.h"
+
+template <int NS> struct GroupOf { static constexpr int G = NS <= 1 ? 1 : NS <= 2 ? 2 : NS <= 4 ? 4 : NS <= 8 ? 8 : NS <= 16 ? 16 : 32; };
+
+__device__ __forceinline__ double shfl_d(unsigned mask, double v, int src, int width)
+{
+    return __shfl_sync(mask, v, src, width);
+}
+
+// ---- in-register LU of one block per group; shared by dgefa_batched and the jac kernels ----
+// a[j] = A(i,j) for this lane's row i (lanes >= NS carry zeros and never win a pivot search).
+// Returns LINPACK's info (uniform over the group); ipv = this lane's ipvt(i+1) (1-based).
+template <int NS>
+__device__ __forceinline__ int group_dgefa(double (&a)[NS], int li, int &ipv)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const unsigned mask = 0xffffffffu;
+    int info = 0;
+    ipv = NS;   // ipvt(n) = n; overwritten for rows k < n below
+#pragma unroll
+    for (int k = 0; k < NS - 1; ++k) {
+        // idamax over rows k..NS-1 of column k: first maximum of |a|
+        double av = (li >= k && li < NS) ? fabs(a[k]) : -1.0;
+        int ai = li;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            double bv = __shfl_xor_sync(mask, av, o, G);
+            int bi = __shfl_xor_sync(mask, ai, o, G);
+            if (bv > av || (bv == av && bi < ai)) {
+                av = bv;
+                ai = bi;
+            }
+        }
+        const int l = ai;                 // uniform in the group
+        if (li == k) ipv = l + 1;
+        const double piv = shfl_d(mask, a[k], l, G);
+        if (piv == 0.0) {                 // zero pivot: column already triangularised
+            info = k + 1;
+            continue;
+        }
+        // interchange a(l,k) <-> a(k,k)
+        const double akk = shfl_d(mask, a[k], k, G);
+        if (l != k) {
+            if (li == l) a[k] = akk;
+            if (li == k) a[k] = piv;
+        }
+        // multipliers (negated)
+        const double t = -1.0 / piv;
+        if (li > k) a[k] = a[k] * t;
+        // row elimination with column indexing
+#pragma unroll
+        for (int j = k + 1; j < NS; ++j) {
+            const double tj = shfl_d(mask, a[j], l, G);
+            const double akj = shfl_d(mask, a[j], k, G);
+            if (l != k) {
+                if (li == l) a[j] = akj;
+                if (li == k) a[j] = tj;
+            }
+            if (li > k) a[j] = a[j] + tj * a[k];
+        }
+    }
+    const double ann = shfl_d(mask, a[NS - 1], NS - 1, G);
+    if (ann == 0.0) info = NS;
+    return info;
+}
+
+// ---- dgesl (job = 0) for one block per group; b = this lane's b(i+1) ----
+template <int NS>
+__device__ __forceinline__ double group_dgesl(const double (&a)[NS], int ipv, int li, double b)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const unsigned mask = 0xffffffffu;
+    // forward: t = b(l); swap; b(k+1:n) += t*a(k+1:n,k)
+#pragma unroll
+    for (int k = 0; k < NS - 1; ++k) {
+        const int l = __shfl_sync(mask, ipv, k, G) - 1;
+        const double t = shfl_d(mask, b, l, G);
+        const double bk = shfl_d(mask, b, k, G);
+        if (l != k) {
+            if (li == l) b = bk;
+            if (li == k) b = t;
+        }
+        if (li > k && li < NS) b = b + t * a[k];
+    }
+    // back: b(k) /= a(k,k); b(1:k-1) += -b(k)*a(1:k-1,k)
+#pragma unroll
+    for (int k = NS - 1; k >= 0; --k) {
+        if (li == k) b = b / a[k];
+        const double t = -shfl_d(mask, b, k, G);
+        if (li < k) b = b + t * a[k];
+    }
+    return b;
+}
+
+template <int NS>
+__device__ __forceinline__ void group_load_block(const double *__restrict__ blk, int li, double (&a)[NS])
+{
+#pragma unroll
+    for (int j = 0; j < NS; ++j) a[j] = (li < NS) ? __ldg(blk + j * NS + li) : 0.0;
+}
+

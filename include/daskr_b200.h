@@ -1,0 +1,178 @@
+/*
+ * daskr_b200.h -- C ABI of the B200-native Krylov path of DASKR.
+ *
+ * Drop-in boundary for HugoMVale/daskr's preconditioned-GMRES inner loop
+ * (dslvk/dspigm/datv/dorth/ddwnrm + the reaction-based block-diagonal
+ * preconditioner jac_rbdpre/psol_rbdpre with batched dgefa/dgesl).  The
+ * reference has no FFI layer: its boundary is the Fortran-77 procedure
+ * convention itself (every argument by reference, INTEGER = int32,
+ * REAL(rk) = double, callbacks = C function pointers).  Every entry point
+ * below keeps that convention so a Fortran host binds it with
+ * `bind(C, name=...)` interfaces (INTEGRATION.md shows the stubs) and names
+ * the reference interface it replaces.
+ *
+ * What changes against the reference: all length-NEQ arrays that the
+ * callbacks see (y, ydot, delta, savr, wk, wght, b, rwp, iwp) are DEVICE
+ * pointers, the solver's own vectors (phi, Krylov basis, LU blocks) live in
+ * device memory owned by the library, and rwork/iwork shrink to their scalar
+ * headers (rwork(1:60), iwork(1:40) + the ID / constraint arrays).  The
+ * y/yprime arguments of dkb_daskr are host arrays (copied in on the initial
+ * call, out at every return) unless DKB_OPT_DEVICE_IO is set.
+ *
+ * Like the reference (SAVE / module variables) the library is
+ * non-reentrant: one problem per process, bound to one GPU.  All functions
+ * return 0 on success or a negative DKB_E_* code (dkb_last_error() has text),
+ * except the Fortran-style subroutines which report through their own
+ * ires / ierr / idid arguments exactly like the routines they replace.
+ */
+#ifndef DASKR_B200_H
+#define DASKR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DKB_VERSION 100
+
+enum {
+    DKB_OK = 0,
+    DKB_E_CUDA = -1,     /* a CUDA runtime call failed */
+    DKB_E_ARG = -2,      /* illegal argument */
+    DKB_E_STATE = -3,    /* call out of order (no context, no setup, ...) */
+    DKB_E_UNSUPPORTED = -4,
+    DKB_E_NCCL = -5
+};
+
+/* options for dkb_set_option */
+enum {
+    DKB_OPT_DEVICE_IO = 1,  /* 1: y/yprime passed to dkb_daskr are device pointers */
+    DKB_OPT_FUSED = 2,      /* 1 (default): use the fused datv kernels for built-in problems */
+    DKB_OPT_MAX_STEPS = 3   /* per-call step limit (reference: 500, src/daskr.f:2057) */
+};
+
+/* ---- callback contracts: src/daskr_new.f90:11-21, 35-53, 55-71 ----
+ * Same argument lists as res_t / jack_t / psol_t; array arguments are device
+ * pointers, scalars are host pointers, rpar/ipar are the caller's host arrays
+ * passed through untouched.  Callbacks enqueue their work on dkb_stream(). */
+typedef void (*dkb_res_t)(const double *t, const double *y, const double *ydot,
+                          const double *cj, double *delta, int *ires,
+                          double *rpar, int *ipar);
+typedef void (*dkb_jack_t)(dkb_res_t res, int *ires, const int *neq, const double *t,
+                           double *y, double *ydot, const double *rewt, double *savr,
+                           double *wk, const double *h, const double *cj,
+                           double *rwp, int *iwp, int *ierr, double *rpar, int *ipar);
+typedef void (*dkb_psol_t)(const int *neq, const double *t, const double *y,
+                           const double *ydot, const double *savr, double *wk,
+                           const double *cj, const double *wght, double *rwp,
+                           int *iwp, double *b, const double *epslin, int *ierr,
+                           double *rpar, int *ipar);
+
+/* ---- context (replaces the reference's SAVE/module state) ---- */
+int dkb_init(int device);            /* create the process-wide context on `device` */
+int dkb_finalize(void);
+const char *dkb_last_error(void);
+int dkb_version(void);
+void *dkb_stream(void);              /* cudaStream_t the library launches on */
+int dkb_set_option(int opt, int64_t value);
+int dkb_sync(void);
+
+/* ---- multi-GPU: y-slab decomposition, NCCL halo exchange + scalar allreduce ----
+ * dkb_comm_unique_id writes an ncclUniqueId (128 bytes) on rank 0; every rank
+ * then calls dkb_comm_init with the same id. */
+int dkb_comm_unique_id(void *id128);
+int dkb_comm_init(const void *id128, int rank, int nranks);
+
+/* ---- setup_rbdpre, src/daskr_rbdpre.f90:102-156 (DMSET2) ----
+ * Same arguments.  my is the GLOBAL number of mesh rows; with a communicator
+ * this rank owns rows [jy0, jy0+myloc) (dkb_slab reports them) and NEQ passed
+ * to dkb_daskr is ns*mx*myloc.  iwork(27:28) (LENWP, LENIWP) are set to 0:
+ * the blocks and pivots live in device memory sized in 64 bits
+ * (ns*ns*mx*my overflows INTEGER at 4096^2 x 20).  If lid != 0 the ID array
+ * is written to iwork(lid+1 : lid+neq) exactly as the reference does. */
+void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *nsd,
+                      const int *lid, int *iwork);
+int dkb_slab(int *jy0, int *myloc);
+
+/* ---- built-in device problems (the user routines of the two examples) ---- */
+/* food web, example/example_web.f90:5-60 (setpar) with np, mx, my at run time */
+int dkb_web_setpar(int np, int mx, int my);
+/* res / jac / psol of example_web.f90:190-224, 301-344, 346-391 (jpre=ipar(1) must
+ * be 1, jbg=ipar(2) must be 0: reaction factor only, no grouping) */
+void dkb_web_res(const double *t, const double *c, const double *cdot, const double *cj,
+                 double *delta, int *ires, double *rpar, int *ipar);
+void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *c,
+                 double *cdot, const double *rewt, double *savr, double *wk,
+                 const double *h, const double *cj, double *rwp, int *iwp, int *ierr,
+                 double *rpar, int *ipar);
+void dkb_web_psol(const int *neq, const double *t, const double *c, const double *cdot,
+                  const double *savr, double *wk, const double *cj, const double *wght,
+                  double *rwp, int *iwp, double *b, const double *epslin, int *ierr,
+                  double *rpar, int *ipar);
+/* cinit, example_web.f90:102-148: fills HOST arrays c, cdot for this rank's slab */
+int dkb_web_cinit(double *c, double *cdot, double pred_ic);
+/* heat, example/example_heat.f90:53-89 with the rbdpre ns=1 pairing of SURVEY 8(d) */
+int dkb_heat_setpar(int m);
+void dkb_heat_res(const double *t, const double *u, const double *udot, const double *cj,
+                  double *delta, int *ires, double *rpar, int *ipar);
+void dkb_heat_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *u,
+                  double *udot, const double *rewt, double *savr, double *wk,
+                  const double *h, const double *cj, double *rwp, int *iwp, int *ierr,
+                  double *rpar, int *ipar);
+void dkb_heat_psol(const int *neq, const double *t, const double *u, const double *udot,
+                   const double *savr, double *wk, const double *cj, const double *wght,
+                   double *rwp, int *iwp, double *b, const double *epslin, int *ierr,
+                   double *rpar, int *ipar);
+int dkb_heat_uinit(double *u, double *udot);
+
+/* ---- DASKR, src/daskr.f:1-3 (Krylov option info(12)=1) ----
+ * Same 21 arguments.  lrw/liw are 64-bit.  rt/nrt/jroot: nrt must be 0 in this
+ * version (rootfinding is host logic outside the hot path). */
+void dkb_daskr(dkb_res_t res, const int *neq, double *t, double *y, double *yprime,
+               const double *tout, int *info, double *rtol, double *atol, int *idid,
+               double *rwork, const int64_t *lrw, int *iwork, const int64_t *liw,
+               double *rpar, int *ipar, dkb_jack_t jac, dkb_psol_t psol, void *rt,
+               const int *nrt, int *jroot);
+
+/* ---- the hot path as separate calls (what a Fortran dnsk/dnedk would bind) ---- */
+/* dslvk, src/daskr_new.f90:3036-3165.  Device arrays y, ydot, savr, x, ewt of
+ * length neq; counters are accumulated into iwm(12,16,20,21) like the reference. */
+void dkb_dslvk(const int *neq, const double *y, const double *t, const double *ydot,
+               const double *savr, double *x, double *ewt, int *iwm, dkb_res_t res,
+               int *ires, dkb_psol_t psol, int *iersl, const double *cj,
+               const double *epslin, const double *sqrtn, const double *rsqrtn,
+               double *rhok, double *rpar, int *ipar);
+/* ddwnrm, src/daskr_new.f90:828-868 (device v, rwt) */
+double dkb_ddwnrm(const int *neq, const double *v, const double *rwt);
+/* jac_rbdpre / psol_rbdpre on device arrays in the reference's bd / ipbd layout
+ * (block p at bd+p*ns*ns column-major, pivots 1-based at ipbd+p*ns),
+ * src/daskr_rbdpre.f90:158-279; rblock is the built-in problem's rate routine */
+void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd);
+
+/* ---- batched LINPACK micro-API (BASELINE config 5), src/linpack.f90:325-520 ----
+ * Device arrays in the bd / ipbd layout.  info_first receives the 1-based index
+ * of the first block whose dgefa info != 0 (0 if none); info (optional, device,
+ * nblk ints) receives every block's dgefa info. */
+int dkb_dgefa_batched(double *bd, int *ipbd, int ns, int64_t nblk, int *info,
+                      int64_t *info_first);
+int dkb_dgesl_batched(const double *bd, const int *ipbd, int ns, int64_t nblk, double *b);
+
+/* ---- device memory helpers for hosts without a CUDA runtime binding ---- */
+int dkb_malloc(void **ptr, int64_t bytes);
+int dkb_free(void *ptr);
+int dkb_memcpy_h2d(void *dst, const void *src, int64_t bytes);
+int dkb_memcpy_d2h(void *dst, const void *src, int64_t bytes);
+int dkb_memset(void *dst, int value, int64_t bytes);
+
+/* ---- measurement hooks (bench.py): kernel-time accumulation by CUDA events ---- */
+int dkb_prof_enable(int on);
+int dkb_prof_reset(void);
+/* name[i] (up to 32 entries of 48 chars), accumulated ms, launch counts */
+int dkb_prof_get(char *names, double *ms, int64_t *launches, int max_entries);
+int64_t dkb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

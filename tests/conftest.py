@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    """CPU oracle (oracle/), built on demand.  Test infrastructure only."""
+    from tests import oracle_py
+
+    return oracle_py.load()
+
+
+@pytest.fixture(scope="session")
+def dk():
+    """The product: daskr_b200 bound to cuda:0.  Fails loudly if the CUDA library is missing."""
+    import daskr_b200
+
+    daskr_b200.lib()
+    daskr_b200.init(0)
+    yield daskr_b200
