@@ -11,6 +11,17 @@ __device__ __forceinline__ double shfl_d(unsigned mask, double v, int src, int w
     return __shfl_sync(mask, v, src, width);
 }
 
+// Lanes of this thread's group.  Several groups share a warp when G < 32 and may diverge from
+// one another (a zero pivot makes one group skip an elimination step), so every shuffle names
+// only its own group's lanes.
+template <int G>
+__device__ __forceinline__ unsigned group_mask()
+{
+    if (G >= 32) return 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << (G & 31)) - 1u) << (lane & ~(unsigned)(G - 1));
+}
+
 // ---- in-register LU of one block per group; shared by dgefa_batched and the jac kernels ----
 // a[j] = A(i,j) for this lane's row i (lanes >= NS carry zeros and never win a pivot search).
 // Returns LINPACK's info (uniform over the group); ipv = this lane's ipvt(i+1) (1-based).
@@ -18,7 +29,7 @@ template <int NS>
 __device__ __forceinline__ int group_dgefa(double (&a)[NS], int li, int &ipv)
 {
     constexpr int G = GroupOf<NS>::G;
-    const unsigned mask = 0xffffffffu;
+    const unsigned mask = group_mask<G>();
     int info = 0;
     ipv = NS;   // ipvt(n) = n; overwritten for rows k < n below
 #pragma unroll
@@ -73,7 +84,7 @@ template <int NS>
 __device__ __forceinline__ double group_dgesl(const double (&a)[NS], int ipv, int li, double b)
 {
     constexpr int G = GroupOf<NS>::G;
-    const unsigned mask = 0xffffffffu;
+    const unsigned mask = group_mask<G>();
     // forward: t = b(l); swap; b(k+1:n) += t*a(k+1:n,k)
 #pragma unroll
     for (int k = 0; k < NS - 1; ++k) {

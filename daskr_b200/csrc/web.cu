@@ -94,7 +94,7 @@ __device__ __forceinline__ double web_rate(double ci, int li, double fac, double
     double r = 0.0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        double cj = __shfl_sync(0xffffffffu, ci, j, G);
+        double cj = __shfl_sync(group_mask<G>(), ci, j, G);
         r = r + cj * sa[j * NS + (li < NS ? li : 0)];
     }
     return ci * (bco * fac + r);
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(128) web_jac_kernel(WebDev w, int nsd, const d
 #pragma unroll
         for (int js = 0; js < NS; ++js) {
             // jac_rbdpre:219-229: del = max(srur*|u_j|, 0.01/rewt_j); perturb; column = (r1-r0)*(-1/del)
-            const double uj = __shfl_sync(0xffffffffu, ci, js, G);
-            const double rj = __shfl_sync(0xffffffffu, rw, js, G);
+            const double uj = __shfl_sync(group_mask<G>(), ci, js, G);
+            const double rj = __shfl_sync(group_mask<G>(), rw, js, G);
             const double del = fmax(w.srur * fabs(uj), 1e-2 / rj);
             const double cpert = (li == js) ? (uj + del) : ci;
             const double fd = -1.0 / del;

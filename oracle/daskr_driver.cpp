@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <vector>
 #include <algorithm>
 
@@ -1317,6 +1318,34 @@ L701:
 /* whole-run helpers                                                   */
 /* ------------------------------------------------------------------ */
 
+/* Optional per-step log for the CPU baseline timing (bench.py): after every BDF step taken in
+ * max_steps mode the run helpers append (wall seconds since the log was armed, NLI, NST). */
+static double *g_steplog = nullptr;
+static long g_steplog_cap = 0, g_steplog_n = 0;
+static double g_steplog_t0 = 0.0;
+static double wall_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+void o_set_steplog(double *buf, long cap)
+{
+    g_steplog = buf;
+    g_steplog_cap = cap;
+    g_steplog_n = 0;
+    g_steplog_t0 = wall_now();
+}
+long o_steplog_count(void) { return g_steplog_n; }
+static void steplog_push(const int *iwork)
+{
+    if (!g_steplog || g_steplog_n >= g_steplog_cap) return;
+    g_steplog[3 * g_steplog_n + 0] = wall_now() - g_steplog_t0;
+    g_steplog[3 * g_steplog_n + 1] = iwork[LNLI - 1];
+    g_steplog[3 * g_steplog_n + 2] = iwork[LNST - 1];
+    ++g_steplog_n;
+}
+
 /* Drive DASKR over a list of output times the way example_web.f90:884-954
  * does: first call computes consistent initial values (info(11)=1,
  * info(14)=1 -> idid=4), then info(11)=0 and integration restarts from the
@@ -1370,6 +1399,7 @@ int o_run_web(int np, int mx, int my, int jpre, double rtol_, double atol_,
             if (idid < 0) break;
             if (max_steps > 0 && idid == 1) {
                 ++steps;
+                steplog_push(iwork.data());
                 if (steps >= max_steps) break;
                 continue;
             }
@@ -1423,6 +1453,7 @@ int o_run_heat(int m, double rtol_, double atol_, int nout, const double *touts,
             if (idid < 0) break;
             if (max_steps > 0 && idid == 1) {
                 ++steps;
+                steplog_push(iwork.data());
                 if (steps >= max_steps) break;
                 continue;
             }

@@ -149,6 +149,8 @@ void o_heat_psol(const int *neq, const double *t, const double *u,
 int o_run_web(int np, int mx, int my, int jpre, double rtol, double atol,
               int nout, const double *touts, double *yout, int *counters,
               double *rhead, long max_steps, double *tfinal);
+void o_set_steplog(double *buf, long cap);   /* (wall s, NLI, NST) per step, max_steps mode */
+long o_steplog_count(void);
 int o_run_heat(int m, double rtol, double atol, int nout, const double *touts,
                double *yout, int *counters, double *rhead, long max_steps,
                double *tfinal);
