@@ -31,6 +31,7 @@ EXPORTS = [
     "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
     "dkb_heat_psol", "dkb_heat_uinit", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
+    "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
     "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
 ]
@@ -64,6 +65,10 @@ def lib():
     L.dkb_comm_unique_id.argtypes = [C.c_void_p]
     L.dkb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.dkb_prof_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.dkb_rbd_lenwp.restype = C.c_int64
+    L.dkb_rbd_leniwp.restype = C.c_int64
+    L.dkb_rbd_to_reference.argtypes = [C.c_void_p] * 4
+    L.dkb_rbd_from_reference.argtypes = [C.c_void_p] * 4
     L.dkb_daskr.restype = None
     L.dkb_daskr.argtypes = [C.c_void_p] * 21
     _lib = L

@@ -496,7 +496,8 @@ void dkb_web_psol(const int *neq, const double *t, const double *cc, const doubl
         *ierr = -1;
         return;
     }
-    lu_dgesl_batched(rwp, iwp, g_ctx->ns, g_ctx->npts, b);
+    // rwp / iwp hold the blocks in the interleaved layout dkb_web_jac wrote (psol_tpp.cu)
+    tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
 }
 
 void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd)
@@ -506,6 +507,43 @@ void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd)
         abort();
     }
     lu_dgesl_batched(bd, ipbd, g_ctx->ns, g_ctx->npts, b);
+}
+
+// Block storage helpers.  dkb_web_jac leaves the LU blocks in the interleaved layout of
+// psol_tpp.cu; these convert to / from the reference's bd / ipbd layout (device arrays).
+int64_t dkb_rbd_lenwp(void)
+{
+    return (g_ctx && g_ctx->rbd_set) ? (g_ctx->ns == 1 ? g_ctx->npts : tpp_lut_doubles(g_ctx->ns, g_ctx->npts)) : 0;
+}
+int64_t dkb_rbd_leniwp(void)
+{
+    return (g_ctx && g_ctx->rbd_set) ? (g_ctx->ns == 1 ? g_ctx->npts : tpp_pt_ints(g_ctx->ns, g_ctx->npts)) : 0;
+}
+int dkb_rbd_to_reference(const double *rwp, const int *iwp, double *bd, int *ipbd)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->rbd_set) return dkb_fail(DKB_E_STATE, "dkb_setup_rbdpre not called");
+    if (c->ns == 1) {
+        CUDA_TRY(cudaMemcpyAsync(bd, rwp, sizeof(double) * c->npts, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(ipbd, iwp, sizeof(int) * c->npts, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        tpp_to_reference(c->ns, c->npts, rwp, iwp, bd, ipbd);
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int dkb_rbd_from_reference(const double *bd, const int *ipbd, double *rwp, int *iwp)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->rbd_set) return dkb_fail(DKB_E_STATE, "dkb_setup_rbdpre not called");
+    if (c->ns == 1) {
+        CUDA_TRY(cudaMemcpyAsync(rwp, bd, sizeof(double) * c->npts, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(iwp, ipbd, sizeof(int) * c->npts, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        tpp_from_reference(c->ns, c->npts, bd, ipbd, rwp, iwp);
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 // ---------------------------------------------------------------- heat

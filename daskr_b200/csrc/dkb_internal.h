@@ -189,6 +189,14 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
 int lu_psol_scaled(const double *bd, const int *ipbd, int ns, i64 nblk, const double *in,
                    const double *wt, double wscale, double *out, int slot);
 
+// thread-per-point block solve over the interleaved LU layout (psol_tpp.cu)
+int tpp_psol(const double *lut, const int *pt, int ns, i64 npts, const double *in, const double *savr,
+             const double *wt, double wscale, double *out, int slot);
+i64 tpp_lut_doubles(int ns, i64 npts);
+i64 tpp_pt_ints(int ns, i64 npts);
+int tpp_from_reference(int ns, i64 npts, const double *bd, const int *ipbd, double *lut, int *pt);
+int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double *bd, int *ipbd);
+
 // ---------------------------------------------------------------- problems (web.cu / heat.cu)
 void web_upload_tables();
 void web_res_launch(const double *c, const double *cdot, double *delta);

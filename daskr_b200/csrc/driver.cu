@@ -96,9 +96,9 @@ static int alloc_solver(DkbCtx *c, i64 neq, int maxl, int kmp, int need_vt, int 
     // for through iwork(27:28)
     {
         i64 lenwp = user_lenwp, leniwp = user_leniwp;
-        if (c->rbd_set) {
-            lenwp += (i64)c->ns * c->ns * c->npts;
-            leniwp += (i64)c->ns * c->npts;
+        if (c->rbd_set) {   // interleaved layout pads the point count to a multiple of 32
+            lenwp += tpp_lut_doubles(c->ns, c->npts);
+            leniwp += tpp_pt_ints(c->ns, c->npts);
         }
         if (lenwp > c->lenwp) {
             if (c->wp) cudaFree(c->wp);

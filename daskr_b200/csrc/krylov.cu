@@ -198,7 +198,10 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
     if (nrsts == 0) {
         ProfScope ps(PROF_PSOL0);
         if (A.fused) {
-            lu_psol_scaled(c->wp, c->iwp, c->ns, c->npts, A.x, A.wt, A.rsqrtn, v[0], S_RNORM);
+            if (c->ns == 1)
+                lu_psol_scaled(c->wp, c->iwp, 1, c->npts, A.x, A.wt, A.rsqrtn, v[0], S_RNORM);
+            else
+                tpp_psol(c->wp, c->iwp, c->ns, c->npts, A.x, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
         } else {
             double *r = v[maxl];   // r is v(:,maxl+1), dslvk:3114
             v_copy(neq, A.x, r);

@@ -202,23 +202,24 @@ __global__ void __launch_bounds__(128) web_jac_kernel(WebDev w, int nsd, const d
         int ipv;
         const int inf = group_dgefa<NS>(a, li, ipv);
         if (live && li < NS) {
-            double *blk = bd + p * (NS * NS);
+            // interleaved layout of psol_tpp.cu: element (i,j) -> ((p/32)*ns*ns + j*ns + i)*32 + p%32
+            double *blk = bd + ((p >> 5) * (NS * NS)) * 32 + (p & 31);
 #pragma unroll
-            for (int j = 0; j < NS; ++j) blk[j * NS + li] = a[j];
-            ipbd[p * NS + li] = ipv;
+            for (int j = 0; j < NS; ++j) blk[(j * NS + li) * 32] = a[j];
+            ipbd[((p >> 5) * NS + li) * 32 + (p & 31)] = ipv;
             if (li == 0 && inf != 0) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
         }
     }
 }
 
-// ---------------------------------------------------------------- K3: fused datv
+// ---------------------------------------------------------------- K3a: datv residual
+// vtemp = G(t, y + v/wght, ydot + cj*v/wght) (datv:3493-3503) without materialising z / ydottemp;
+// the block solve, "- savr" and "* wght" (datv:3509-3518) follow in tpp_psol (psol_tpp.cu).
 template <int NS>
-__global__ void __launch_bounds__(256) web_datv_kernel(WebDev w, const double *__restrict__ v,
-                                                       const double *__restrict__ wt, double wscale,
-                                                       const double *__restrict__ y, const double *__restrict__ ydot,
-                                                       const double *__restrict__ savr, double cj,
-                                                       const double *__restrict__ bd, const int *__restrict__ ipbd,
-                                                       double *__restrict__ vnext)
+__global__ void __launch_bounds__(256) web_resdatv_kernel(WebDev w, const double *__restrict__ v,
+                                                          const double *__restrict__ wt, double wscale,
+                                                          const double *__restrict__ y, const double *__restrict__ ydot,
+                                                          double cj, double *__restrict__ vtemp)
 {
     GROUP_LOOP_PROLOGUE(NS)
     StateDatv S{y, v, wt, wscale};
@@ -227,18 +228,12 @@ __global__ void __launch_bounds__(256) web_datv_kernel(WebDev w, const double *_
         const bool live = p < npts;
         if (!live) p = npts - 1;
         const i64 idx = p * NS + lic;
-        // issue the LU stream first: it is the bulk of the bytes and independent of the stencil
-        double a[NS];
-        group_load_block<NS>(bd + p * (NS * NS), li, a);
-        const int ipv = (li < NS) ? __ldg(ipbd + idx) : 1;
         const double wgt = wscale * __ldg(wt + idx);
         const double vtmp = __ldg(v + idx) / wgt;          // vtemp = v/wght
         const double zi = __ldg(y + idx) + vtmp;           // z = y + vtemp
         const double ydt = __ldg(ydot + idx) + vtmp * cj;  // ydottemp = ydot + vtemp*cj
-        double d = web_point_res<NS>(w, S, p, li, ydt, zi, web_fac(w, p), bco, cxi, cyi, sa);
-        d = d - __ldg(savr + idx);                         // z = vtemp - savr   (:3509)
-        d = group_dgesl<NS>(a, ipv, li, (li < NS) ? d : 0.0);   // psol_rbdpre
-        if (live && li < NS) vnext[idx] = d * wgt;         // z = z*wght         (:3518)
+        const double d = web_point_res<NS>(w, S, p, li, ydt, zi, web_fac(w, p), bco, cxi, cyi, sa);
+        if (live && li < NS) vtemp[idx] = d;
     }
 }
 
@@ -302,8 +297,10 @@ void web_datv_fused(const double *v, const double *wt, double wscale, const doub
     WebDev w = make_webdev();
     const i64 npts = x->npts;
     const size_t sh = sizeof(double) * w.ns * w.ns;
-#define CALL(N) web_datv_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 256, 8), 256, sh, x->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)
+    double *vtemp = x->z;
+#define CALL(N) web_resdatv_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 256, 8), 256, sh, x->stream>>>(w, v, wt, wscale, y, ydot, cj, vtemp)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
     COUNT_LAUNCH();
+    tpp_psol(bd, ipbd, w.ns, npts, vtemp, savr, wt, wscale, vnext, -1);
 }

@@ -145,10 +145,17 @@ void dkb_dslvk(const int *neq, const double *y, const double *t, const double *y
                double *rhok, double *rpar, int *ipar);
 /* ddwnrm, src/daskr_new.f90:828-868 (device v, rwt) */
 double dkb_ddwnrm(const int *neq, const double *v, const double *rwt);
-/* jac_rbdpre / psol_rbdpre on device arrays in the reference's bd / ipbd layout
- * (block p at bd+p*ns*ns column-major, pivots 1-based at ipbd+p*ns),
- * src/daskr_rbdpre.f90:158-279; rblock is the built-in problem's rate routine */
+/* psol_rbdpre, src/daskr_rbdpre.f90:253-279, on device arrays in the reference's bd / ipbd
+ * layout (block p at bd+p*ns*ns column-major, pivots 1-based at ipbd+p*ns) */
 void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd);
+/* The rwp / iwp arrays the jac / psol callbacks see hold the same LU factors and pivots in a
+ * tile-interleaved order (32 mesh points per tile, see psol_tpp.cu) so that the per-point
+ * solves stream at HBM speed.  dkb_rbd_lenwp / leniwp give their lengths (doubles / ints);
+ * the two converters map between that order and the reference's bd / ipbd (device arrays). */
+int64_t dkb_rbd_lenwp(void);
+int64_t dkb_rbd_leniwp(void);
+int dkb_rbd_to_reference(const double *rwp, const int *iwp, double *bd, int *ipbd);
+int dkb_rbd_from_reference(const double *bd, const int *ipbd, double *rwp, int *iwp);
 
 /* ---- batched LINPACK micro-API (BASELINE config 5), src/linpack.f90:325-520 ----
  * Device arrays in the bd / ipbd layout.  info_first receives the 1-based index

@@ -103,24 +103,41 @@ def test_web_jac_psol_bit_exact(dk, oracle, np_, mx, my):
     bd_o, ip_o, ierr_o = oracle.web_jac(c, rewt, cj, ns)
     _web_setup_gpu(dk, np_, mx, my)
     npts = mx * my
+    L = dk.lib()
     dc, dw = DeviceBuffer.from_host(c), DeviceBuffer.from_host(rewt)
+    # the jac callback writes rwp / iwp in the tile-interleaved order; convert for comparison
+    dwp, diwp = DeviceBuffer(8 * L.dkb_rbd_lenwp()), DeviceBuffer(4 * L.dkb_rbd_leniwp())
     dbd, dip = DeviceBuffer(8 * ns * ns * npts), DeviceBuffer(4 * ns * npts)
     t, cjc, ires, ierr, neq, h = C.c_double(0.0), C.c_double(cj), C.c_int(0), C.c_int(0), C.c_int(c.size), C.c_double(0)
     ipar = np.array([1, 0], dtype=np.int32)
-    dk.lib().dkb_web_jac(None, _ref(ires), _ref(neq), _ref(t), dc.ptr, None, dw.ptr, None, None, _ref(h), _ref(cjc),
-                         dbd.ptr, dip.ptr, _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+    L.dkb_web_jac(None, _ref(ires), _ref(neq), _ref(t), dc.ptr, None, dw.ptr, None, None, _ref(h), _ref(cjc),
+                  dwp.ptr, diwp.ptr, _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+    assert L.dkb_rbd_to_reference(dwp.ptr, diwp.ptr, dbd.ptr, dip.ptr) == 0
     bd_g = dbd.to_host(np.float64, (npts, ns * ns))
     ip_g = dip.to_host(np.int32, (npts, ns))
     assert ierr.value == ierr_o == 0
     assert np.array_equal(ip_g, ip_o), "pivot indices must be bit-exact"
     assert np.array_equal(bd_g, bd_o), "max rel diff %.3e" % np.max(np.abs(bd_g - bd_o) / np.maximum(np.abs(bd_o), 1e-300))
-    # psol on those blocks
+    # psol on those blocks: reference-layout entry point and the callback on the interleaved arrays
     b = np.random.default_rng(2).standard_normal(c.size)
     x_o = oracle.psol_rbdpre(b, bd_o, ip_o)
     db = DeviceBuffer.from_host(b)
-    dk.lib().dkb_psol_rbdpre(db.ptr, dbd.ptr, dip.ptr)
-    assert dk.lib().dkb_sync() == 0
+    L.dkb_psol_rbdpre(db.ptr, dbd.ptr, dip.ptr)
+    assert L.dkb_sync() == 0
     assert np.array_equal(db.to_host(np.float64, b.shape), x_o)
+    db2 = DeviceBuffer.from_host(b)
+    eps = C.c_double(0.0)
+    L.dkb_web_psol(_ref(neq), _ref(t), None, None, None, None, _ref(cjc), None, dwp.ptr, diwp.ptr, db2.ptr, _ref(eps),
+                   _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+    assert L.dkb_sync() == 0 and ierr.value == 0
+    assert np.array_equal(db2.to_host(np.float64, b.shape), x_o)
+    # round trip reference -> interleaved -> reference
+    dwp2, diwp2 = DeviceBuffer(8 * L.dkb_rbd_lenwp()), DeviceBuffer(4 * L.dkb_rbd_leniwp())
+    dbd2, dip2 = DeviceBuffer(8 * ns * ns * npts), DeviceBuffer(4 * ns * npts)
+    assert L.dkb_rbd_from_reference(dbd.ptr, dip.ptr, dwp2.ptr, diwp2.ptr) == 0
+    assert L.dkb_rbd_to_reference(dwp2.ptr, diwp2.ptr, dbd2.ptr, dip2.ptr) == 0
+    assert np.array_equal(dbd2.to_host(np.float64, (npts, ns * ns)), bd_o)
+    assert np.array_equal(dip2.to_host(np.int32, (npts, ns)), ip_o)
 
 
 def test_ddwnrm(dk, oracle):
