@@ -79,6 +79,58 @@ __device__ __forceinline__ int group_dgefa(double (&a)[NS], int li, int &ipv)
     return info;
 }
 
+// ---- dgefa with logical row interchanges ----
+// Same factorisation, same arithmetic, but the data of a row never leaves its lane: LINPACK's
+// interchange of rows l and k (columns >= k only, src/linpack.f90:404-420) becomes an update of
+// the lanes' logical row numbers `r`.  That removes the two exchange shuffles per eliminated
+// element; what is left is one broadcast of the pivot row's element per column.  The pivot search
+// (idamax: first maximum) runs on the integer image of |a| with three warp reductions instead of a
+// five-round shuffle butterfly.  Column k is final once step k is done; `store(col, pos, value)`
+// is called for every lane with pos = the row LINPACK would hold that value in.
+template <int NS, class Store>
+__device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &ipv, Store store)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const unsigned mask = group_mask<G>();
+    const unsigned lane0 = (threadIdx.x & 31u) & ~(unsigned)(G - 1);   // first warp lane of this group
+    int info = 0;
+    int r = li;   // logical (LINPACK) row currently held by this lane, for columns >= k
+    ipv = NS;
+#pragma unroll
+    for (int k = 0; k < NS - 1; ++k) {
+        const bool cand = (li < NS) && (r >= k);
+        const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(fabs(a[k])) : 0ull;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_max_sync(mask, hi);
+        const unsigned mlo = __reduce_max_sync(mask, (cand && hi == mhi) ? lo : 0u);
+        const unsigned l = __reduce_min_sync(mask, (cand && hi == mhi && lo == mlo) ? (unsigned)r : 0xffu);
+        const unsigned who = __ballot_sync(mask, cand && r == (int)l);
+        const int pl = (int)(__ffs(who) - 1 - lane0);   // group-relative lane of the pivot row
+        if (li == k) ipv = (int)l + 1;
+        const double piv = shfl_d(mask, a[k], pl, G);
+        if (piv == 0.0) {   // zero pivot: no interchange, column left as is (linpack.f90:394-397)
+            info = k + 1;
+            store(k, r, a[k]);
+            continue;
+        }
+        if (r == (int)l) r = k;
+        else if (r == k) r = (int)l;
+        const double t = -1.0 / piv;
+        if (r > k) a[k] = a[k] * t;   // multipliers (negated)
+        store(k, r, a[k]);
+#pragma unroll
+        for (int j = k + 1; j < NS; ++j) {
+            const double tj = shfl_d(mask, a[j], pl, G);
+            if (r > k) a[j] = a[j] + tj * a[k];
+        }
+    }
+    store(NS - 1, r, a[NS - 1]);
+    const unsigned wl = __ballot_sync(mask, (li < NS) && r == NS - 1);
+    const double ann = shfl_d(mask, a[NS - 1], (int)(__ffs(wl) - 1 - lane0), G);
+    if (ann == 0.0) info = NS;
+    return info;
+}
+
 // ---- dgesl (job = 0) for one block per group; b = this lane's b(i+1) ----
 template <int NS>
 __device__ __forceinline__ double group_dgesl(const double (&a)[NS], int ipv, int li, double b)

@@ -1,23 +1,28 @@
 // web.cu -- device kernels of the food-web problem (example/example_web.f90)
-//   K4  residual           res:190-224 + f:226-269 + rates:271-299
-//   K5  block Jacobian     jac:301-344 -> jac_rbdpre (src/daskr_rbdpre.f90:158-251) + dgefa
-//   K3  fused datv         datv (src/daskr_new.f90:3493-3518) with res and psol_rbdpre inlined
+//   K4/K3a  residual        res:190-224 + f:226-269 + rates:271-299, evaluated either at (c, cdot)
+//                           or, for datv (src/daskr_new.f90:3493-3503), at the perturbed state
+//                           z = y + v/wght, ydottemp = ydot + cj*v/wght formed on the fly
+//   K5      block Jacobian  jac:301-344 -> jac_rbdpre (src/daskr_rbdpre.f90:158-251) + dgefa
+// The block solve that completes datv (psol_rbdpre, "- savr", "* wght") is psol_tpp.cu.
 //
-// Mapping: one sub-warp group (G = 2^ceil(log2 ns) lanes) per mesh point, lane i
-// = species i.  Unknown (i,jx,jy) sits at i + ns*(jx-1) + ns*mx*(jy-1), so a
-// group touches ns*8 contiguous bytes per array and per neighbour; x-neighbours
-// are the adjacent groups' lines (L1), y-neighbours one mesh row away (L2).
-// The ns x ns interaction sum uses shuffle broadcasts of the point's
-// concentrations against a shared-memory copy of acoef; the LU blocks of the
-// point stream through registers (lu.cu layout) exactly once per launch.
-// Mesh rows are slab-decomposed: rows outside the slab are read from the halo
-// rows just before / after the local array, global edges use the reference's
-// mirrored Neumann differences.
+// Residual: one CTA per 16 x 8 tile of mesh points, one thread per unknown (species fastest, so
+// every global access is a coalesced 2560-byte row segment).  The state values of the tile and of
+// its 5-point-stencil halo are staged once in shared memory -- for datv that includes the divide
+// v/wght, done 1.375x per unknown instead of 5x -- and both the stencil and the ns x ns interaction
+// sum read them from there.  Mesh rows are slab-decomposed: rows outside the slab come from the
+// halo rows stored just before / after the local array, global edges use the reference's mirrored
+// Neumann differences.
+//
+// Jacobian: one sub-warp group per mesh point, lane i = row i of the block.  The point's
+// concentrations and this lane's row of acoef are hoisted into registers, so the ns finite-
+// difference columns need no shuffles; the LU factorisation keeps rows where they are and tracks
+// LINPACK's row interchanges as a logical permutation (lu_device.cuh), which leaves one shuffle
+// broadcast per eliminated column.  Arithmetic is the reference's, operation for operation.
 #include "dkb_internal.h"
 #include <math.h>
 #include <string.h>
 
-#include "lu_device.cuh"   // group_dgefa / group_dgesl / group_load_block
+#include "lu_device.cuh"   // group_dgefa_track
 
 struct WebDev {
     int ns, np, mx, my, jy0, my_g, has_lo, has_hi;
@@ -72,96 +77,115 @@ void web_upload_tables()
     dkb_cuda_check("web_upload_tables");
 }
 
-// ---- accessors for the state the residual is evaluated at ----
-struct StatePlain {       // G(t, c, cdot)
-    const double *c;
-    __device__ __forceinline__ double operator()(i64 idx) const { return __ldg(c + idx); }
-};
-struct StateDatv {        // z = y + v/wght, wght = wscale*wt   (datv:3493-3498)
-    const double *y, *v, *wt;
-    double wscale;
-    __device__ __forceinline__ double operator()(i64 idx) const
-    {
-        return __ldg(y + idx) + __ldg(v + idx) / (wscale * __ldg(wt + idx));
-    }
-};
-
-// rates:286-297 for lane li given the point's concentrations (ci own, broadcast by shuffle)
-template <int NS>
-__device__ __forceinline__ double web_rate(double ci, int li, double fac, double bco, const double *sa)
+__device__ __forceinline__ double web_fac_xy(const WebDev &w, int jx, int jyg)
 {
-    constexpr int G = GroupOf<NS>::G;
-    double r = 0.0;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-        double cj = __shfl_sync(group_mask<G>(), ci, j, G);
-        r = r + cj * sa[j * NS + (li < NS ? li : 0)];
-    }
-    return ci * (bco * fac + r);
-}
-
-// f:241-267 + res:213-220 at one point; returns delta for lane li
-template <int NS, class State>
-__device__ __forceinline__ double web_point_res(const WebDev &w, const State &S, i64 p, int li, double cdot_i,
-                                                double ci, double fac, double bco, double cxi, double cyi,
-                                                const double *sa)
-{
-    const int lic = li < NS ? li : 0;
-    const i64 mxns = (i64)w.mx * NS;
-    const int jyl = (int)(p / w.mx);          // local row, 0-based
-    const int jx = (int)(p - (i64)jyl * w.mx);
-    const int jyg = w.jy0 + jyl;              // global row, 0-based
-    const i64 ici = p * NS + lic;
-    // mirrored Neumann offsets (f:243-254); slab edges read the halo rows
-    i64 idyu = mxns, idyl = mxns, idxu = NS, idxl = NS;
-    if (jyg == w.my_g - 1) idyu = -mxns;
-    if (jyg == 0) idyl = -mxns;
-    if (jx == w.mx - 1) idxu = -NS;
-    if (jx == 0) idxl = -NS;
-    const double cyl = S(ici - idyl), cyu = S(ici + idyu), cxl = S(ici - idxl), cxu = S(ici + idxu);
-    const double R = web_rate<NS>(ci, li, fac, bco, sa);
-    const double dcyli = ci - cyl, dcyui = cyu - ci, dcxli = ci - cxl, dcxui = cxu - ci;
-    const double f = cyi * (dcyui - dcyli) + cxi * (dcxui - dcxli) + R;
-    return (lic >= w.np) ? -f : (cdot_i - f);
-}
-
-__device__ __forceinline__ double web_fac(const WebDev &w, i64 p)
-{
-    const int jyl = (int)(p / w.mx);
-    const int jx = (int)(p - (i64)jyl * w.mx);
-    const int jyg = w.jy0 + jyl;
     const double y = jyg * w.dy, x = jx * w.dx;
     return 1.0 + w.alpha * x * y + w.beta * __ldg(w.sx + jx) * __ldg(w.sy + jyg);
 }
 
-#define GROUP_LOOP_PROLOGUE(NS)                                                            \
-    constexpr int G = GroupOf<NS>::G;                                                      \
-    const int li = threadIdx.x % G;                                                        \
-    const int lic = li < NS ? li : 0;                                                      \
-    const i64 gpb = blockDim.x / G;                                                        \
-    const i64 ngroups = (i64)gridDim.x * gpb;                                              \
-    const i64 npts = (i64)w.mx * w.my;                                                     \
-    const i64 nloop = (npts + ngroups - 1) / ngroups;                                      \
-    extern __shared__ double sa[];                                                         \
-    for (int t = threadIdx.x; t < NS * NS; t += blockDim.x) sa[t] = w.acoef[t];            \
-    __syncthreads();                                                                       \
-    const double bco = w.bcoef[lic], cxi = w.cox[lic], cyi = w.coy[lic];
+// ---------------------------------------------------------------- K4 / K3a: tiled residual
+#define RT_TX 16
+#define RT_TY 8
+#define RT_THREADS 256
 
-// ---------------------------------------------------------------- K4: residual
-template <int NS>
-__global__ void __launch_bounds__(256) web_res_kernel(WebDev w, const double *__restrict__ c,
-                                                      const double *__restrict__ cdot, double *__restrict__ delta)
+template <int NS, bool DATV>
+__global__ void __launch_bounds__(RT_THREADS)
+web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
+                   const double *__restrict__ y, const double *__restrict__ ydot, double cj,
+                   double *__restrict__ out)
 {
-    GROUP_LOOP_PROLOGUE(NS)
-    StatePlain S{c};
-    for (i64 it = 0; it < nloop; ++it) {
-        i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
-        const bool live = p < npts;
-        if (!live) p = npts - 1;
-        const i64 idx = p * NS + lic;
-        const double ci = S(idx);
-        const double d = web_point_res<NS>(w, S, p, li, __ldg(cdot + idx), ci, web_fac(w, p), bco, cxi, cyi, sa);
-        if (live && li < NS) delta[idx] = d;
+    constexpr int ZX = RT_TX + 2, ZY = RT_TY + 2;
+    constexpr int ROWU = RT_TX * NS;            // unknowns per tile row
+    constexpr int NU = RT_TY * ROWU;            // unknowns per tile
+    constexpr int PER = (NU + RT_THREADS - 1) / RT_THREADS;
+    constexpr int NHALO = (2 * RT_TX + 2 * RT_TY) * NS;
+    extern __shared__ double sm[];
+    double *sa = sm;                            // acoef, column-major
+    double *sb = sa + NS * NS;                  // bcoef | cox | coy
+    double *Z = sb + 3 * NS;                    // state values, [ZY][ZX][NS]
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NS * NS; t += RT_THREADS) sa[t] = w.acoef[t];
+    for (int t = tid; t < 3 * NS; t += RT_THREADS) sb[t] = w.bcoef[t];   // bcoef, cox, coy are contiguous
+
+    const int tiles_x = (w.mx + RT_TX - 1) / RT_TX;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * RT_TX, y0 = ty * RT_TY;
+    const i64 mxns = (i64)w.mx * NS;
+
+    // state value at global unknown g (may index the halo rows before/after the local array)
+    auto state = [&](i64 g) -> double {
+        if (DATV) return __ldg(y + g) + __ldg(v + g) / (wscale * __ldg(wt + g));   // z = y + v/wght
+        return __ldg(y + g);
+    };
+
+    // ---- phase 1a: this thread's own unknowns (kept in registers across the barrier)
+    double ydt[PER];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+        const int q = tid + RT_THREADS * m;
+        ydt[m] = 0.0;
+        if (q < NU) {
+            const int ry = q / ROWU, rem = q - ry * ROWU;
+            const int x = rem / NS, i = rem - x * NS;
+            const int gy = y0 + ry, gx = x0 + x;
+            if (gy < w.my && gx < w.mx) {
+                const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
+                double z;
+                if (DATV) {
+                    const double wgt = wscale * __ldg(wt + g);
+                    const double vtmp = __ldg(v + g) / wgt;        // vtemp = v/wght        (datv:3493)
+                    z = __ldg(y + g) + vtmp;                       // z = y + vtemp         (:3498)
+                    ydt[m] = __ldg(ydot + g) + vtmp * cj;          // ydottemp = ydot+vtemp*cj (:3497)
+                } else {
+                    z = __ldg(y + g);
+                    ydt[m] = __ldg(ydot + g);
+                }
+                Z[((ry + 1) * ZX + (x + 1)) * NS + i] = z;
+            }
+        }
+    }
+    // ---- phase 1b: the stencil halo of the tile (no corners)
+    for (int h = tid; h < NHALO; h += RT_THREADS) {
+        const int hp = h / NS, i = h - hp * NS;
+        int ry, x;
+        if (hp < RT_TX) { ry = -1; x = hp; }
+        else if (hp < 2 * RT_TX) { ry = RT_TY; x = hp - RT_TX; }
+        else if (hp < 2 * RT_TX + RT_TY) { ry = hp - 2 * RT_TX; x = -1; }
+        else { ry = hp - 2 * RT_TX - RT_TY; x = RT_TX; }
+        const int gy = y0 + ry, gx = x0 + x;
+        const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
+        if (rowok && gx >= 0 && gx < w.mx && (ry < 0 || ry >= RT_TY || gy < w.my))
+            Z[((ry + 1) * ZX + (x + 1)) * NS + i] = state((i64)gy * mxns + (i64)gx * NS + i);
+    }
+    __syncthreads();
+
+    // ---- phase 2: f:241-267, rates:286-297, res:213-220
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+        const int q = tid + RT_THREADS * m;
+        if (q >= NU) continue;
+        const int ry = q / ROWU, rem = q - ry * ROWU;
+        const int x = rem / NS, i = rem - x * NS;
+        const int gy = y0 + ry, gx = x0 + x;
+        if (gy >= w.my || gx >= w.mx) continue;
+        const int jyg = w.jy0 + gy;
+        const int pt = (ry + 1) * ZX + (x + 1);
+        // mirrored Neumann neighbours (f:243-254)
+        const int pyl = (jyg == 0) ? pt + ZX : pt - ZX;
+        const int pyu = (jyg == w.my_g - 1) ? pt - ZX : pt + ZX;
+        const int pxl = (gx == 0) ? pt + 1 : pt - 1;
+        const int pxu = (gx == w.mx - 1) ? pt - 1 : pt + 1;
+        const double *zp = Z + pt * NS;
+        const double ci = zp[i];
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) r = r + zp[j] * sa[j * NS + i];
+        const double fac = web_fac_xy(w, gx, jyg);
+        const double R = ci * (sb[i] * fac + r);
+        const double dcyli = ci - Z[pyl * NS + i], dcyui = Z[pyu * NS + i] - ci;
+        const double dcxli = ci - Z[pxl * NS + i], dcxui = Z[pxu * NS + i] - ci;
+        const double f = sb[2 * NS + i] * (dcyui - dcyli) + sb[NS + i] * (dcxui - dcxli) + R;
+        out[(i64)gy * mxns + (i64)gx * NS + i] = (i >= w.np) ? -f : (ydt[m] - f);
     }
 }
 
@@ -172,8 +196,20 @@ __global__ void __launch_bounds__(128) web_jac_kernel(WebDev w, int nsd, const d
                                                       double *__restrict__ bd, int *__restrict__ ipbd,
                                                       int *first_flag)
 {
-    GROUP_LOOP_PROLOGUE(NS)
-    (void)cxi; (void)cyi;
+    constexpr int G = GroupOf<NS>::G;
+    const unsigned mask = group_mask<G>();
+    const int li = threadIdx.x % G;
+    const int lic = li < NS ? li : 0;
+    const i64 gpb = blockDim.x / G;
+    const i64 ngroups = (i64)gridDim.x * gpb;
+    const i64 npts = (i64)w.mx * w.my;
+    const i64 nloop = (npts + ngroups - 1) / ngroups;
+    // this lane's row of acoef and its bcoef: rates:290-297 needs sum_j c_j*acoef(i,j)
+    double arow[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) arow[j] = w.acoef[j * NS + lic];
+    const double bco = w.bcoef[lic];
+
     for (i64 it = 0; it < nloop; ++it) {
         i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
         const bool live = p < npts;
@@ -181,59 +217,49 @@ __global__ void __launch_bounds__(128) web_jac_kernel(WebDev w, int nsd, const d
         const i64 idx = p * NS + lic;
         const double ci = __ldg(c + idx);
         const double rw = __ldg(rewt + idx);
-        const double fac = web_fac(w, p);
-        const double r0 = web_rate<NS>(ci, li, fac, bco, sa);
+        const int jyl = (int)(p / w.mx);
+        const int jx = (int)(p - (i64)jyl * w.mx);
+        const double fac = web_fac_xy(w, jx, w.jy0 + jyl);
+        // the point's concentrations and weights, broadcast once
+        double cb[NS], del[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            cb[j] = __shfl_sync(mask, ci, j, G);
+            const double rj = __shfl_sync(mask, rw, j, G);
+            del[j] = fmax(w.srur * fabs(cb[j]), 1e-2 / rj);   // jac_rbdpre:222
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) r = r + cb[j] * arow[j];
+        const double r0 = ci * (bco * fac + r);               // what res left in rpar (f:250)
         double a[NS];
 #pragma unroll
         for (int js = 0; js < NS; ++js) {
-            // jac_rbdpre:219-229: del = max(srur*|u_j|, 0.01/rewt_j); perturb; column = (r1-r0)*(-1/del)
-            const double uj = __shfl_sync(group_mask<G>(), ci, js, G);
-            const double rj = __shfl_sync(group_mask<G>(), rw, js, G);
-            const double del = fmax(w.srur * fabs(uj), 1e-2 / rj);
-            const double cpert = (li == js) ? (uj + del) : ci;
-            const double fd = -1.0 / del;
-            const double r1 = web_rate<NS>(cpert, li, fac, bco, sa);
+            // jac_rbdpre:219-229: perturb u_js, column = (r1 - r0)*(-1/del), restore
+            const double up = cb[js] + del[js];
+            const double fd = -1.0 / del[js];
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s = s + ((j == js) ? up : cb[j]) * arow[j];
+            const double cown = (li == js) ? up : ci;
+            const double r1 = cown * (bco * fac + s);
             a[js] = (r1 - r0) * fd;
         }
         // add cj*I_d (jac_rbdpre:240-244)
 #pragma unroll
         for (int j = 0; j < NS; ++j)
             if (j == li && li < nsd) a[j] = a[j] + cj;
+        // LU with logical row interchanges; column k is final after step k and is stored at its
+        // LINPACK position pos right away (interleaved layout of psol_tpp.cu)
+        double *blk = bd + ((p >> 5) * (NS * NS)) * 32 + (p & 31);
         int ipv;
-        const int inf = group_dgefa<NS>(a, li, ipv);
+        const int inf = group_dgefa_track<NS>(a, li, ipv, [&](int col, int pos, double val) {
+            if (live && li < NS) blk[(col * NS + pos) * 32] = val;
+        });
         if (live && li < NS) {
-            // interleaved layout of psol_tpp.cu: element (i,j) -> ((p/32)*ns*ns + j*ns + i)*32 + p%32
-            double *blk = bd + ((p >> 5) * (NS * NS)) * 32 + (p & 31);
-#pragma unroll
-            for (int j = 0; j < NS; ++j) blk[(j * NS + li) * 32] = a[j];
             ipbd[((p >> 5) * NS + li) * 32 + (p & 31)] = ipv;
             if (li == 0 && inf != 0) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
         }
-    }
-}
-
-// ---------------------------------------------------------------- K3a: datv residual
-// vtemp = G(t, y + v/wght, ydot + cj*v/wght) (datv:3493-3503) without materialising z / ydottemp;
-// the block solve, "- savr" and "* wght" (datv:3509-3518) follow in tpp_psol (psol_tpp.cu).
-template <int NS>
-__global__ void __launch_bounds__(256) web_resdatv_kernel(WebDev w, const double *__restrict__ v,
-                                                          const double *__restrict__ wt, double wscale,
-                                                          const double *__restrict__ y, const double *__restrict__ ydot,
-                                                          double cj, double *__restrict__ vtemp)
-{
-    GROUP_LOOP_PROLOGUE(NS)
-    StateDatv S{y, v, wt, wscale};
-    for (i64 it = 0; it < nloop; ++it) {
-        i64 p = (i64)blockIdx.x * gpb + threadIdx.x / G + it * ngroups;
-        const bool live = p < npts;
-        if (!live) p = npts - 1;
-        const i64 idx = p * NS + lic;
-        const double wgt = wscale * __ldg(wt + idx);
-        const double vtmp = __ldg(v + idx) / wgt;          // vtemp = v/wght
-        const double zi = __ldg(y + idx) + vtmp;           // z = y + vtemp
-        const double ydt = __ldg(ydot + idx) + vtmp * cj;  // ydottemp = ydot + vtemp*cj
-        const double d = web_point_res<NS>(w, S, p, li, ydt, zi, web_fac(w, p), bco, cxi, cyi, sa);
-        if (live && li < NS) vtemp[idx] = d;
     }
 }
 
@@ -265,16 +291,27 @@ static int grp_grid(i64 npts, int G, int block, int per_sm)
         abort();                                                                            \
     }
 
+template <int NS, bool DATV>
+static void restile_launch(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+                           const double *ydot, double cj, double *out)
+{
+    static bool attr_set = false;
+    const size_t sh = sizeof(double) * (NS * NS + 3 * NS + (RT_TX + 2) * (RT_TY + 2) * NS);
+    if (!attr_set && sh > 48 * 1024) {
+        cudaFuncSetAttribute(web_restile_kernel<NS, DATV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        attr_set = true;
+    }
+    const int tiles = ((w.mx + RT_TX - 1) / RT_TX) * ((w.my + RT_TY - 1) / RT_TY);
+    web_restile_kernel<NS, DATV><<<tiles, RT_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, out);
+    COUNT_LAUNCH();
+}
+
 void web_res_launch(const double *c, const double *cdot, double *delta)
 {
-    DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
-    const i64 npts = x->npts;
-    const size_t sh = sizeof(double) * w.ns * w.ns;
-#define CALL(N) web_res_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 256, 8), 256, sh, x->stream>>>(w, c, cdot, delta)
+#define CALL(N) restile_launch<N, false>(w, nullptr, nullptr, 1.0, c, cdot, 0.0, delta)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
-    COUNT_LAUNCH();
 }
 
 void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd, int *d_first_flag)
@@ -282,25 +319,24 @@ void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, 
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
     const i64 npts = x->npts;
-    const size_t sh = sizeof(double) * w.ns * w.ns;
     const int nsd = x->nsd;
-#define CALL(N) web_jac_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 128, 8), 128, sh, x->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)
+#define CALL(N) web_jac_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 128, 8), 128, 0, x->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
     COUNT_LAUNCH();
 }
 
+// datv (src/daskr_new.f90:3429-3520) for the built-in problem: vtemp = G(z, ydottemp) into the
+// ydottemp slot (free here: ydottemp is never materialised), then the block solve with the
+// "- savr" and "* wght" statements folded into its load / store phases.
 void web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
                     const double *savr, double cj, const double *bd, const int *ipbd, double *vnext)
 {
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
-    const i64 npts = x->npts;
-    const size_t sh = sizeof(double) * w.ns * w.ns;
     double *vtemp = x->z;
-#define CALL(N) web_resdatv_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 256, 8), 256, sh, x->stream>>>(w, v, wt, wscale, y, ydot, cj, vtemp)
+#define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, vtemp)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
-    COUNT_LAUNCH();
-    tpp_psol(bd, ipbd, w.ns, npts, vtemp, savr, wt, wscale, vnext, -1);
+    tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, savr, wt, wscale, vnext, -1);
 }
