@@ -84,108 +84,107 @@ __device__ __forceinline__ double web_fac_xy(const WebDev &w, int jx, int jyg)
 }
 
 // ---------------------------------------------------------------- K4 / K3a: tiled residual
-#define RT_TX 16
+// Tile = RT<NS>::TX mesh points wide, RT_TY rows high; one thread per (point-in-row, species),
+// i.e. NS*TX threads, each walking the RT_TY rows of the tile with its species fixed -- so its
+// row of acoef, bcoef, cox, coy live in registers and the interaction sum costs one (broadcast)
+// shared-memory read per term.
 #define RT_TY 8
-#define RT_THREADS 256
+template <int NS> struct RT {
+    static constexpr int TX = NS >= 16 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;
+    static constexpr int THREADS = NS * TX;
+};
 
 template <int NS, bool DATV>
-__global__ void __launch_bounds__(RT_THREADS)
+__global__ void __launch_bounds__(RT<NS>::THREADS)
 web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
                    const double *__restrict__ y, const double *__restrict__ ydot, double cj,
                    double *__restrict__ out)
 {
-    constexpr int ZX = RT_TX + 2, ZY = RT_TY + 2;
-    constexpr int ROWU = RT_TX * NS;            // unknowns per tile row
-    constexpr int NU = RT_TY * ROWU;            // unknowns per tile
-    constexpr int PER = (NU + RT_THREADS - 1) / RT_THREADS;
-    constexpr int NHALO = (2 * RT_TX + 2 * RT_TY) * NS;
-    extern __shared__ double sm[];
-    double *sa = sm;                            // acoef, column-major
-    double *sb = sa + NS * NS;                  // bcoef | cox | coy
-    double *Z = sb + 3 * NS;                    // state values, [ZY][ZX][NS]
+    constexpr int TX = RT<NS>::TX, THREADS = RT<NS>::THREADS;
+    constexpr int ZX = TX + 2;
+    constexpr int NHALO = (2 * TX + 2 * RT_TY) * NS;
+    extern __shared__ double Z[];               // state values, [RT_TY+2][ZX][NS]
     const int tid = threadIdx.x;
-    for (int t = tid; t < NS * NS; t += RT_THREADS) sa[t] = w.acoef[t];
-    for (int t = tid; t < 3 * NS; t += RT_THREADS) sb[t] = w.bcoef[t];   // bcoef, cox, coy are contiguous
+    const int x = tid / NS, i = tid - x * NS;   // this thread's point within a tile row, its species
+    double arow[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) arow[j] = __ldg(w.acoef + j * NS + i);
+    const double bco = __ldg(w.bcoef + i), cxi = __ldg(w.cox + i), cyi = __ldg(w.coy + i);
 
-    const int tiles_x = (w.mx + RT_TX - 1) / RT_TX;
+    const int tiles_x = (w.mx + TX - 1) / TX;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int x0 = tx * RT_TX, y0 = ty * RT_TY;
+    const int x0 = tx * TX, y0 = ty * RT_TY;
+    const int gx = x0 + x;
     const i64 mxns = (i64)w.mx * NS;
 
-    // state value at global unknown g (may index the halo rows before/after the local array)
-    auto state = [&](i64 g) -> double {
-        if (DATV) return __ldg(y + g) + __ldg(v + g) / (wscale * __ldg(wt + g));   // z = y + v/wght
-        return __ldg(y + g);
-    };
-
-    // ---- phase 1a: this thread's own unknowns (kept in registers across the barrier)
-    double ydt[PER];
+    // ---- phase 1a: this thread's own unknowns, one per tile row (kept in registers across the barrier)
+    double ydt[RT_TY];
 #pragma unroll
-    for (int m = 0; m < PER; ++m) {
-        const int q = tid + RT_THREADS * m;
-        ydt[m] = 0.0;
-        if (q < NU) {
-            const int ry = q / ROWU, rem = q - ry * ROWU;
-            const int x = rem / NS, i = rem - x * NS;
-            const int gy = y0 + ry, gx = x0 + x;
-            if (gy < w.my && gx < w.mx) {
-                const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
-                double z;
-                if (DATV) {
-                    const double wgt = wscale * __ldg(wt + g);
-                    const double vtmp = __ldg(v + g) / wgt;        // vtemp = v/wght        (datv:3493)
-                    z = __ldg(y + g) + vtmp;                       // z = y + vtemp         (:3498)
-                    ydt[m] = __ldg(ydot + g) + vtmp * cj;          // ydottemp = ydot+vtemp*cj (:3497)
-                } else {
-                    z = __ldg(y + g);
-                    ydt[m] = __ldg(ydot + g);
-                }
-                Z[((ry + 1) * ZX + (x + 1)) * NS + i] = z;
+    for (int ry = 0; ry < RT_TY; ++ry) {
+        const int gy = y0 + ry;
+        ydt[ry] = 0.0;
+        if (gy < w.my && gx < w.mx) {
+            const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
+            double z;
+            if (DATV) {
+                const double wgt = wscale * __ldg(wt + g);
+                const double vtmp = __ldg(v + g) / wgt;        // vtemp = v/wght            (datv:3493)
+                z = __ldg(y + g) + vtmp;                       // z = y + vtemp             (:3498)
+                ydt[ry] = __ldg(ydot + g) + vtmp * cj;         // ydottemp = ydot + vtemp*cj (:3497)
+            } else {
+                z = __ldg(y + g);
+                ydt[ry] = __ldg(ydot + g);
             }
+            Z[((ry + 1) * ZX + (x + 1)) * NS + i] = z;
         }
     }
     // ---- phase 1b: the stencil halo of the tile (no corners)
-    for (int h = tid; h < NHALO; h += RT_THREADS) {
-        const int hp = h / NS, i = h - hp * NS;
-        int ry, x;
-        if (hp < RT_TX) { ry = -1; x = hp; }
-        else if (hp < 2 * RT_TX) { ry = RT_TY; x = hp - RT_TX; }
-        else if (hp < 2 * RT_TX + RT_TY) { ry = hp - 2 * RT_TX; x = -1; }
-        else { ry = hp - 2 * RT_TX - RT_TY; x = RT_TX; }
-        const int gy = y0 + ry, gx = x0 + x;
-        const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
-        if (rowok && gx >= 0 && gx < w.mx && (ry < 0 || ry >= RT_TY || gy < w.my))
-            Z[((ry + 1) * ZX + (x + 1)) * NS + i] = state((i64)gy * mxns + (i64)gx * NS + i);
+    for (int h = tid; h < NHALO; h += THREADS) {
+        const int hp = h / NS, hi = h - hp * NS;
+        int ry, hx;
+        if (hp < TX) { ry = -1; hx = hp; }
+        else if (hp < 2 * TX) { ry = RT_TY; hx = hp - TX; }
+        else if (hp < 2 * TX + RT_TY) { ry = hp - 2 * TX; hx = -1; }
+        else { ry = hp - 2 * TX - RT_TY; hx = TX; }
+        const int gy = y0 + ry, hgx = x0 + hx;
+        const bool top_bottom = (ry < 0 || ry >= RT_TY);
+        const bool rowok = top_bottom ? ((gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi))
+                                      : (gy < w.my);
+        if (rowok && hgx >= 0 && hgx < w.mx) {
+            const i64 g = (i64)gy * mxns + (i64)hgx * NS + hi;   // may address the slab halo rows
+            double z = __ldg(y + g);
+            if (DATV) z = z + __ldg(v + g) / (wscale * __ldg(wt + g));
+            Z[((ry + 1) * ZX + (hx + 1)) * NS + hi] = z;
+        }
     }
     __syncthreads();
 
     // ---- phase 2: f:241-267, rates:286-297, res:213-220
+    if (gx >= w.mx) return;
+    const int dxl = (gx == 0) ? 1 : -1;           // mirrored Neumann neighbours (f:243-254)
+    const int dxu = (gx == w.mx - 1) ? -1 : 1;
+    const double sxv = __ldg(w.sx + gx);
+    const double xx = gx * w.dx;
 #pragma unroll
-    for (int m = 0; m < PER; ++m) {
-        const int q = tid + RT_THREADS * m;
-        if (q >= NU) continue;
-        const int ry = q / ROWU, rem = q - ry * ROWU;
-        const int x = rem / NS, i = rem - x * NS;
-        const int gy = y0 + ry, gx = x0 + x;
-        if (gy >= w.my || gx >= w.mx) continue;
+    for (int ry = 0; ry < RT_TY; ++ry) {
+        const int gy = y0 + ry;
+        if (gy >= w.my) break;
         const int jyg = w.jy0 + gy;
         const int pt = (ry + 1) * ZX + (x + 1);
-        // mirrored Neumann neighbours (f:243-254)
         const int pyl = (jyg == 0) ? pt + ZX : pt - ZX;
         const int pyu = (jyg == w.my_g - 1) ? pt - ZX : pt + ZX;
-        const int pxl = (gx == 0) ? pt + 1 : pt - 1;
-        const int pxu = (gx == w.mx - 1) ? pt - 1 : pt + 1;
         const double *zp = Z + pt * NS;
         const double ci = zp[i];
         double r = 0.0;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) r = r + zp[j] * sa[j * NS + i];
-        const double fac = web_fac_xy(w, gx, jyg);
-        const double R = ci * (sb[i] * fac + r);
+        for (int j = 0; j < NS; ++j) r = r + zp[j] * arow[j];
+        const double yy = jyg * w.dy;
+        const double fac = 1.0 + w.alpha * xx * yy + w.beta * sxv * __ldg(w.sy + jyg);
+        const double R = ci * (bco * fac + r);
         const double dcyli = ci - Z[pyl * NS + i], dcyui = Z[pyu * NS + i] - ci;
-        const double dcxli = ci - Z[pxl * NS + i], dcxui = Z[pxu * NS + i] - ci;
-        const double f = sb[2 * NS + i] * (dcyui - dcyli) + sb[NS + i] * (dcxui - dcxli) + R;
-        out[(i64)gy * mxns + (i64)gx * NS + i] = (i >= w.np) ? -f : (ydt[m] - f);
+        const double dcxli = ci - Z[(pt + dxl) * NS + i], dcxui = Z[(pt + dxu) * NS + i] - ci;
+        const double f = cyi * (dcyui - dcyli) + cxi * (dcxui - dcxli) + R;
+        out[(i64)gy * mxns + (i64)gx * NS + i] = (i >= w.np) ? -f : (ydt[ry] - f);
     }
 }
 
@@ -296,13 +295,14 @@ static void restile_launch(const WebDev &w, const double *v, const double *wt, d
                            const double *ydot, double cj, double *out)
 {
     static bool attr_set = false;
-    const size_t sh = sizeof(double) * (NS * NS + 3 * NS + (RT_TX + 2) * (RT_TY + 2) * NS);
+    constexpr int TX = RT<NS>::TX;
+    const size_t sh = sizeof(double) * ((TX + 2) * (RT_TY + 2) * NS);
     if (!attr_set && sh > 48 * 1024) {
         cudaFuncSetAttribute(web_restile_kernel<NS, DATV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         attr_set = true;
     }
-    const int tiles = ((w.mx + RT_TX - 1) / RT_TX) * ((w.my + RT_TY - 1) / RT_TY);
-    web_restile_kernel<NS, DATV><<<tiles, RT_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, out);
+    const int tiles = ((w.mx + TX - 1) / TX) * ((w.my + RT_TY - 1) / RT_TY);
+    web_restile_kernel<NS, DATV><<<tiles, RT<NS>::THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, out);
     COUNT_LAUNCH();
 }
 
