@@ -290,19 +290,35 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    bytes_per_launch = neq * (8 * (6 + ns) + 4)
-    roof = {"bound": "hbm", "kernel": "web_datv_kernel<20> (fused datv: residual + block solve)", "achieved": None,
-            "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": bytes_per_launch, "launches": dat["count"]}
-    if dat["count"] > 0 and dat["ms"] > 0:
-        ach = bytes_per_launch / (dat["ms"] / dat["count"] * 1e-3) / 1e9
+    # Dominant kernel: tpp_psol_kernel<20> (psol_rbdpre fused with "- savr" and "* wght").  Algorithmic
+    # bytes per launch: the LU block (8*ns per unknown) and pivots (4) once, plus the vectors it must
+    # touch: in, wt, out (+ savr inside datv).  It runs once per Krylov iteration inside datv and once
+    # per dspigm call as the prologue psol (no savr).
+    tpp = prof.get("tpp_psol_kernel", {"ms": 0.0, "count": 0})
+    n_datv = dat["count"]
+    n_psol0 = max(tpp["count"] - n_datv, 0)
+    b_datv = neq * (8 * ns + 4 + 8 * 4)
+    b_psol0 = neq * (8 * ns + 4 + 8 * 3)
+    roof = {"bound": "hbm", "kernel": "tpp_psol_kernel<20> (psol_rbdpre block solve + datv's '- savr' / '* wght')",
+            "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": b_datv, "launches": tpp["count"]}
+    if tpp["count"] > 0 and tpp["ms"] > 0:
+        ach = (n_datv * b_datv + n_psol0 * b_psol0) / (tpp["ms"] * 1e-3) / 1e9
         roof["achieved"] = ach
         roof["frac"] = ach / peak
-        roof["avg_launch_ms"] = dat["ms"] / dat["count"]
-        roof["share_of_step_time"] = dat["ms"] / ms
+        roof["avg_launch_ms"] = tpp["ms"] / tpp["count"]
+        roof["share_of_step_time"] = tpp["ms"] / ms
+    # the whole Jacobian-vector product (residual kernel + block solve) against the bytes a single
+    # fully fused kernel would have to move, N*[8*(6+ns)+4] (SURVEY.md 8d "phase A")
+    if dat["count"] > 0 and dat["ms"] > 0:
+        b_phase = neq * (8 * (6 + ns) + 4)
+        ach = b_phase / (dat["ms"] / dat["count"] * 1e-3) / 1e9
+        roof["datv_phase"] = {"kernels": "web_restile_kernel<20,true> + tpp_psol_kernel<20>", "algorithmic_bytes": b_phase,
+                              "avg_ms": dat["ms"] / dat["count"], "achieved": ach, "frac": ach / peak,
+                              "share_of_step_time": dat["ms"] / ms}
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        key = "web_datv_ns20_%dx%d" % (mx, myloc)
+        key = "tpp_psol_ns20_%dx%d" % (mx, myloc)
         if key in tr:
             roof["traffic"] = tr[key]["dram_bytes_per_launch"]
             roof["traffic_source"] = tr[key].get("source")

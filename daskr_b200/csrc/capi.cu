@@ -128,7 +128,7 @@ void halo_exchange3(double *a, double *b, double *cc)
 }
 
 // ---------------------------------------------------------------- profiling
-static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo"};
+static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo", "tpp_psol_kernel", "resdatv_kernel"};
 void prof_begin(int slot)
 {
     DkbCtx *c = g_ctx;

@@ -39,7 +39,7 @@ struct ProfSlot {
     double ms;
     i64 launches;
 };
-enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO,
+enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV,
        PROF_NSLOTS };
 
 // ---------------------------------------------------------------- context

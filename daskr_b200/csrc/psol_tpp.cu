@@ -187,11 +187,14 @@ int tpp_psol(const double *lut, const int *pt, int ns, i64 npts, const double *i
     i64 ntile = (npts + TPP_THREADS - 1) / TPP_THREADS;
     int grid = (int)std::min<i64>(ntile, 148 * 4);
     double *res = slot >= 0 ? c->d_scal + slot : nullptr;
+    {
+        ProfScope ps(PROF_TPP);   // events around this one launch: the roofline kernel of bench.py
 #define CALL(N)                                                                                              \
     tpp_psol_kernel<N><<<grid, TPP_THREADS, 0, c->stream>>>(lut, pt, npts, in, savr, wt, wscale, out,        \
                                                             slot >= 0 ? 1 : 0, c->d_part, c->d_ticket, res)
-    TPP_DISPATCH(ns, CALL)
+        TPP_DISPATCH(ns, CALL)
 #undef CALL
+    }
     COUNT_LAUNCH();
     if (slot >= 0) allreduce_sum(slot, 1);
     return 0;

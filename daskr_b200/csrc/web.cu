@@ -335,8 +335,11 @@ void web_datv_fused(const double *v, const double *wt, double wscale, const doub
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
     double *vtemp = x->z;
+    {
+        ProfScope ps(PROF_RESDATV);
 #define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, vtemp)
-    WEB_DISPATCH(w.ns, CALL)
+        WEB_DISPATCH(w.ns, CALL)
 #undef CALL
+    }
     tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, savr, wt, wscale, vnext, -1);
 }
