@@ -1,0 +1,66 @@
+"""Multi-GPU parity check (run under torchrun on a GPU box; not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py
+
+Every rank owns a y-slab, halo rows travel by NCCL send/recv, dots and norms by NCCL allreduce.
+Rank 0 gathers the slabs and compares with the oracle's full-mesh run (within 10x tolerance in
+the WRMS norm; counters side by side).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+    import daskr_b200 as dk
+
+    dk.init(local)
+    dk.comm_init_from_torch(rank, world)
+    ok = True
+    cases = [("web", 1, 24, 26, True), ("web", 1, 24, 26, False), ("web", 10, 16, 18, True), ("heat", 0, 30, 0, True)]
+    for kind, np_, mx, my, fused in cases:
+        if kind == "web":
+            touts = [1e-8, 1e-6, 1e-4, 1e-3, 1e-2]
+            g = dk.solve_web(np_, mx, my, touts, fused=fused)
+            rtol, atol = 1e-5, 1e-5
+        else:
+            touts = [0.01 * 2 ** n for n in range(6)]
+            g = dk.solve_heat(mx, touts, fused=fused)
+            rtol, atol = 0.0, 1e-5
+        ys = g["y"]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ys)
+        if rank == 0:
+            from tests import oracle_py
+
+            orc = oracle_py.load()
+            o = orc.run_web(np_, mx, my, touts) if kind == "web" else orc.run_heat(mx, touts)
+            full = np.concatenate(gathered, axis=1)
+            assert full.shape == o["y"].shape, (full.shape, o["y"].shape)
+            w = 1.0 / (rtol * np.abs(o["y"]) + atol)
+            err = np.sqrt(np.mean(((full - o["y"]) * w) ** 2, axis=1))
+            cg, co = g["counters"][-1], o["counters"][-1]
+            good = g["idid"] == o["idid"] == 3 and err.max() <= 10.0
+            ok = ok and good
+            print("%s np=%d %dx%d fused=%s world=%d: max wrms(diff)/tol=%.3e  NST %d/%d NNI %d/%d NLI %d/%d NJE %d/%d -> %s"
+                  % (kind, np_, mx, my, fused, world, err.max(), cg[10], co[10], cg[18], co[18], cg[19], co[19], cg[12], co[12],
+                     "OK" if good else "FAIL"), flush=True)
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
