@@ -123,7 +123,9 @@ web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restr
     for (int ry = 0; ry < RT_TY; ++ry) {
         const int gy = y0 + ry;
         ydt[ry] = 0.0;
-        if (gy < w.my && gx < w.mx) {
+        // rows of the tile beyond the slab: the first one is the upper neighbour's ghost row and is
+        // needed by the last local row when the slab height is not a multiple of the tile height
+        if ((gy < w.my || (gy == w.my && w.has_hi)) && gx < w.mx) {
             const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
             double z;
             if (DATV) {
