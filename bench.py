@@ -191,7 +191,7 @@ def run_ours(args):
     neq_g = ns * mx * my
     iwork = np.zeros(40 + neq, dtype=np.int32)
     dk.setup_rbdpre(mx, my, ns, NP_SPECIES, 40, iwork)
-    dk.web_setpar(NP_SPECIES, mx, my)
+    dk.web_setpar(NP_SPECIES, mx, my, ay=float(world))   # N unit squares stacked in y: same mesh spacing per GPU
     stream = torch.cuda.ExternalStream(dk.lib().dkb_stream())
 
     def barrier():

@@ -28,7 +28,8 @@ PSOL_T = C.CFUNCTYPE(None, *([C.c_void_p] * 15))
 # every symbol include/daskr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "dkb_init", "dkb_finalize", "dkb_last_error", "dkb_version", "dkb_stream", "dkb_set_option", "dkb_sync",
-    "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_res",
+    "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
+    "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
     "dkb_heat_psol", "dkb_heat_uinit", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
@@ -54,6 +55,7 @@ def lib():
     L.dkb_launch_count.restype = C.c_int64
     L.dkb_set_option.argtypes = [C.c_int, C.c_int64]
     L.dkb_web_cinit.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+    L.dkb_web_setpar_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
     L.dkb_heat_uinit.argtypes = [C.c_void_p, C.c_void_p]
     L.dkb_dgefa_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
     L.dkb_dgesl_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p]
@@ -150,8 +152,8 @@ def slab():
     return jy0.value, my.value
 
 
-def web_setpar(np_, mx, my):
-    _check(lib().dkb_web_setpar(int(np_), int(mx), int(my)), "dkb_web_setpar")
+def web_setpar(np_, mx, my, ay=1.0):
+    _check(lib().dkb_web_setpar_ex(int(np_), int(mx), int(my), float(ay)), "dkb_web_setpar")
 
 
 def web_cinit(neq, pred_ic=1e5):

@@ -333,7 +333,14 @@ int dkb_slab(int *jy0, int *myloc)
 
 // ---------------------------------------------------------------- food web
 // setpar, example/example_web.f90:19-58
-int dkb_web_setpar(int np, int mx, int my)
+int dkb_web_setpar(int np, int mx, int my) { return dkb_web_setpar_ex(np, mx, my, 1.0); }
+
+// Same problem on the rectangle [0,1] x [0,ay]: the rate factor and the initial profile are
+// functions of the normalised coordinate y/ay, the diffusion stencil uses the true spacing
+// dy = ay/(my-1).  ay = 1 is exactly the reference's setpar; ay = N with my = N*m keeps the mesh
+// spacing of the m x m unit-square problem when the mesh is grown along y over N GPUs (weak
+// scaling runs of bench.py).
+int dkb_web_setpar_ex(int np, int mx, int my, double ay)
 {
     DkbCtx *c = g_ctx;
     if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
@@ -347,7 +354,7 @@ int dkb_web_setpar(int np, int mx, int my)
     w.mx = mx;
     w.my = my;
     w.ax = 1.0;
-    w.ay = 1.0;
+    w.ay = ay;
     w.aa = 1.0;
     w.ee = 1e4;
     w.gg = 0.5e-6;
@@ -358,6 +365,7 @@ int dkb_web_setpar(int np, int mx, int my)
     w.beta = 3e2;
     w.dx = w.ax / (mx - 1);
     w.dy = w.ay / (my - 1);
+    w.dyn = w.dy / w.ay;
     const int ns = w.ns;
 #define ACOEF(i, j) w.acoef[((j) - 1) * ns + ((i) - 1)]
     for (int j = 1; j <= np; ++j) {
@@ -394,8 +402,8 @@ int dkb_web_cinit(double *cout, double *cdotout, double pred_ic)
     const double pi = 4 * atan(1.0);
     auto cval = [&](int jy /*global, 1-based*/, int jx, int i) -> double {
         if (i > np) return pred_ic;
-        double y = (jy - 1) * w.dy;
-        double argy = 16 * y * y * (w.ay - y) * (w.ay - y);
+        double y = (jy - 1) * w.dyn;
+        double argy = 16 * y * y * (1.0 - y) * (1.0 - y);
         double x = (jx - 1) * w.dx;
         double argx = 16 * x * x * (w.ax - x) * (w.ax - x);
         return 10.0 + i * argx * argy;
@@ -404,7 +412,7 @@ int dkb_web_cinit(double *cout, double *cdotout, double pred_ic)
     for (int jl = 1; jl <= c->my; ++jl) {
         const int jy = c->jy0 + jl;
         const int jyu = (jy == myg) ? jy - 1 : jy + 1, jyl = (jy == 1) ? jy + 1 : jy - 1;
-        const double y = (jy - 1) * w.dy;
+        const double y = (jy - 1) * w.dyn;
         for (int jx = 1; jx <= mx; ++jx) {
             const int jxu = (jx == mx) ? jx - 1 : jx + 1, jxl = (jx == 1) ? jx + 1 : jx - 1;
             const double x = (jx - 1) * w.dx;

@@ -25,6 +25,7 @@ enum { DKB_PROB_NONE = 0, DKB_PROB_WEB = 1, DKB_PROB_HEAT = 2 };
 struct WebPar {                  // module web_par, example/example_web.f90:5-60
     int np, ns, mx, my;          // my = GLOBAL rows
     double aa, ee, gg, bb, dprey, dpred, alpha, beta, ax, ay, dx, dy;
+    double dyn;                  // dy/ay: row spacing in the normalised coordinate the rate factor and IC use
     double acoef[DKB_NS_MAX * DKB_NS_MAX];   // column-major (k,i) at [i*ns+k]
     double bcoef[DKB_NS_MAX], cox[DKB_NS_MAX], coy[DKB_NS_MAX];
 };

@@ -45,7 +45,7 @@ static WebDev make_webdev()
     w.alpha = c->web.alpha;
     w.beta = c->web.beta;
     w.dx = c->web.dx;
-    w.dy = c->web.dy;
+    w.dy = c->web.dyn;                 // normalised row spacing (== dy for the unit square)
     w.srur = 1.4901161193847656e-08;   // sqrt(epsilon(one)) = 2^-26, daskr_rbdpre.f90:129
     const double *tab = c->d_sx;       // [sx(mx) | sy(my_g) | acoef(ns*ns) | bcoef | cox | coy]
     w.sx = tab;
@@ -66,7 +66,7 @@ void web_upload_tables()
     const double pi = 4 * atan(1.0);
     std::vector<double> tab;
     for (int jx = 1; jx <= c->mx; ++jx) tab.push_back(sin(4 * pi * ((jx - 1) * p.dx)));
-    for (int jy = 1; jy <= c->my_g; ++jy) tab.push_back(sin(4 * pi * ((jy - 1) * p.dy)));
+    for (int jy = 1; jy <= c->my_g; ++jy) tab.push_back(sin(4 * pi * ((jy - 1) * p.dyn)));
     for (int i = 0; i < p.ns * p.ns; ++i) tab.push_back(p.acoef[i]);
     for (int i = 0; i < p.ns; ++i) tab.push_back(p.bcoef[i]);
     for (int i = 0; i < p.ns; ++i) tab.push_back(p.cox[i]);

@@ -98,6 +98,8 @@ int dkb_slab(int *jy0, int *myloc);
 /* ---- built-in device problems (the user routines of the two examples) ---- */
 /* food web, example/example_web.f90:5-60 (setpar) with np, mx, my at run time */
 int dkb_web_setpar(int np, int mx, int my);
+/* the same problem on [0,1] x [0,ay] (fields in y/ay, true spacing in the stencil); ay=1 is setpar */
+int dkb_web_setpar_ex(int np, int mx, int my, double ay);
 /* res / jac / psol of example_web.f90:190-224, 301-344, 346-391 (jpre=ipar(1) must
  * be 1, jbg=ipar(2) must be 0: reaction factor only, no grouping) */
 void dkb_web_res(const double *t, const double *c, const double *cdot, const double *cj,
