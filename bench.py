@@ -317,9 +317,23 @@ def run_ours(args):
         roof["datv_phase"] = {"kernels": "web_restile_kernel<20,true> + tpp_psol_kernel<20>", "algorithmic_bytes": b_phase,
                               "avg_ms": dat["ms"] / dat["count"], "achieved": ach, "frac": ach / peak,
                               "share_of_step_time": dat["ms"] / ms}
+    key = "tpp_psol_ns20_%dx%d" % (mx, myloc)
+    # With the single-kernel datv (default when mx % 32 == 0) the dominant kernel is
+    # web_datv_single_kernel<20>: residual at the perturbed state + block solve, N*[8*(6+ns)+4] bytes.
+    one = prof.get("datv_single_kernel", {"ms": 0.0, "count": 0})
+    if one["count"] > 0 and one["ms"] > 0:
+        b_one = neq * (8 * (6 + ns) + 4)
+        ach = b_one / (one["ms"] / one["count"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "web_datv_single_kernel<20> (fused datv: perturbed-state residual + psol_rbdpre block solve)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_one, "launches": one["count"], "avg_launch_ms": one["ms"] / one["count"],
+                "share_of_step_time": one["ms"] / ms}
+        if tpp["count"] > 0:
+            roof["psol_prologue_kernel"] = {"kernel": "tpp_psol_kernel<20>", "avg_launch_ms": tpp["ms"] / tpp["count"],
+                                            "achieved": b_psol0 / (tpp["ms"] / tpp["count"] * 1e-3) / 1e9}
+        key = "web_datv_single_ns20_%dx%d" % (mx, myloc)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-        key = "tpp_psol_ns20_%dx%d" % (mx, myloc)
         if key in tr:
             roof["traffic"] = tr[key]["dram_bytes_per_launch"]
             roof["traffic_source"] = tr[key].get("source")

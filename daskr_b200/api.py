@@ -321,7 +321,7 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     iwork = np.zeros(40 + neq, dtype=np.int32)
     setup_rbdpre(mx, my, ns, np_, 40, iwork)
     web_setpar(np_, mx, my)
-    set_option(OPT_FUSED, 1 if fused else 0)
+    set_option(OPT_FUSED, 2 if fused is True else int(fused))   # 0 callbacks, 1 two kernels, 2 single fused kernel
     info = np.zeros(20, dtype=np.int32)
     info[11] = 1  # info(12): Krylov
     info[14] = 1  # info(15): jac supplied
@@ -375,7 +375,7 @@ def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=Tru
     iwork = np.zeros(40, dtype=np.int32)
     setup_rbdpre(m + 2, m + 2, 1, 1, 0, iwork)
     heat_setpar(m)
-    set_option(OPT_FUSED, 1 if fused else 0)
+    set_option(OPT_FUSED, 2 if fused is True else int(fused))   # 0 callbacks, 1 two kernels, 2 single fused kernel
     info = np.zeros(20, dtype=np.int32)
     info[11] = 1
     info[14] = 1

@@ -128,7 +128,7 @@ void halo_exchange3(double *a, double *b, double *cc)
 }
 
 // ---------------------------------------------------------------- profiling
-static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo", "tpp_psol_kernel", "resdatv_kernel"};
+static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo", "tpp_psol_kernel", "resdatv_kernel", "datv_single_kernel"};
 void prof_begin(int slot)
 {
     DkbCtx *c = g_ctx;
@@ -249,7 +249,7 @@ int dkb_set_option(int opt, int64_t value)
     if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
     switch (opt) {
     case DKB_OPT_DEVICE_IO: g_ctx->opt_device_io = value != 0; break;
-    case DKB_OPT_FUSED: g_ctx->opt_fused = value != 0; break;
+    case DKB_OPT_FUSED: g_ctx->opt_fused = (int)value; break;   // 0 callbacks, 1 two kernels, 2 single kernel
     case DKB_OPT_MAX_STEPS: g_ctx->opt_max_steps = value > 0 ? value : 500; break;
     default: return dkb_fail(DKB_E_ARG, "unknown option %d", opt);
     }

@@ -40,7 +40,7 @@ struct ProfSlot {
     double ms;
     i64 launches;
 };
-enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV,
+enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV, PROF_DATV1,
        PROF_NSLOTS };
 
 // ---------------------------------------------------------------- context
@@ -50,7 +50,7 @@ struct DkbCtx {
     char err[512] = {0};
     // options
     int opt_device_io = 0;
-    int opt_fused = 1;
+    int opt_fused = 2;           // 0: datv through the callbacks, 1: residual + solve kernels, 2: single fused kernel
     i64 opt_max_steps = 500;
 
     // communicator (NCCL, loaded lazily)

@@ -24,13 +24,9 @@
 
 #include "lu_device.cuh"   // group_dgefa_track
 
-struct WebDev {
-    int ns, np, mx, my, jy0, my_g, has_lo, has_hi;
-    double alpha, beta, dx, dy, srur;
-    const double *acoef, *bcoef, *cox, *coy, *sx, *sy;   // device tables
-};
+#include "web_dev.cuh"
 
-static WebDev make_webdev()
+WebDev make_webdev()
 {
     DkbCtx *c = g_ctx;
     WebDev w;
@@ -74,6 +70,7 @@ void web_upload_tables()
     if (c->d_sx) cudaFree(c->d_sx);
     cudaMalloc(&c->d_sx, tab.size() * sizeof(double));
     cudaMemcpy(c->d_sx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    datv_fused_upload_tables(p);
     dkb_cuda_check("web_upload_tables");
 }
 
@@ -336,6 +333,8 @@ void web_datv_fused(const double *v, const double *wt, double wscale, const doub
 {
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
+    // one kernel when the mesh allows it (warp = 32 consecutive points of a row = one LU tile)
+    if (x->opt_fused >= 2 && web_datv_single(w, v, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)) return;
     double *vtemp = x->z;
     {
         ProfScope ps(PROF_RESDATV);

@@ -1,0 +1,18 @@
+// web_dev.cuh -- device-side view of the food-web problem parameters (shared by web.cu and
+// datv_fused.cu).  Built by make_webdev() from the context (module web_par, example_web.f90:5-60).
+#pragma once
+#include "dkb_internal.h"
+
+struct WebDev {
+    int ns, np, mx, my, jy0, my_g, has_lo, has_hi;
+    double alpha, beta, dx, dy, srur;
+    const double *acoef, *bcoef, *cox, *coy, *sx, *sy;   // device tables
+};
+
+WebDev make_webdev();
+// copies acoef / bcoef / cox / coy into the constant bank the fused datv kernel reads them from
+void datv_fused_upload_tables(const WebPar &p);
+// single-kernel datv; returns false if the mesh / ns is not eligible (caller falls back)
+bool web_datv_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+                     const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
+                     double *vnext);

@@ -174,7 +174,7 @@ def _report(tag, touts, g, o, rtol, atol):
     return worst
 
 
-@pytest.mark.parametrize("mx,fused", [(20, True), (20, False), (40, True)])
+@pytest.mark.parametrize("mx,fused", [(20, True), (20, False), (40, True), (32, 2), (32, 1), (64, 2)])
 def test_solve_web_parity(dk, oracle, mx, fused):
     """BASELINE config A: food web ns=2 as shipped (20x20 of the original, 40x40 of the modern file),
     reaction-factor preconditioner (jpre=1), IC calculation on, outputs 1e-8 .. 1."""
@@ -229,3 +229,11 @@ def test_fused_equals_unfused_bitwise_state(dk):
     b = dk.solve_web(1, 20, 20, [1e-8], fused=False)
     assert np.array_equal(a["c0"], b["c0"])
     assert np.array_equal(a["counters"][0], b["counters"][0])
+    # 32-wide meshes take the single-kernel datv (level 2); it must equal the two-kernel path
+    # (level 1) and the callback path (level 0) bit for bit, including after real time steps
+    for np_, mx, my in ((1, 32, 32), (10, 32, 12), (4, 64, 9)):
+        runs = [dk.solve_web(np_, mx, my, [1e-8, 1e-5, 1e-3], fused=lvl) for lvl in (2, 1, 0)]
+        for r in runs[1:]:
+            assert np.array_equal(runs[0]["c0"], r["c0"])
+            assert np.array_equal(runs[0]["y"], r["y"])
+            assert np.array_equal(runs[0]["counters"], r["counters"])
