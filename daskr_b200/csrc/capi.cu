@@ -712,6 +712,36 @@ int dkb_memset(void *dst, int value, int64_t bytes)
     return 0;
 }
 
+// ---------------------------------------------------------------- tuning hooks (not part of the reference surface)
+// Times `reps` launches of the datv path at fused level `level` / kernel variant `variant` on the
+// solver state left by the last dkb_daskr call (CUDA events on the library stream).
+int dkb_debug_time_datv(int level, int variant, int reps, double *ms)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena || c->problem != DKB_PROB_WEB) return dkb_fail(DKB_E_STATE, "needs a food-web solver state");
+    const int save_l = c->opt_fused, save_v = c->debug_variant;
+    c->opt_fused = level;
+    c->debug_variant = variant;
+    const double rs = 1.0 / sqrt((double)c->neq_g);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1]);   // warm
+    cudaEventRecord(a, c->stream);
+    for (int i = 0; i < reps; ++i) web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1]);
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, a, b);
+    *ms = t / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    c->opt_fused = save_l;
+    c->debug_variant = save_v;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------- measurement hooks
 int dkb_prof_enable(int on)
 {

@@ -23,8 +23,6 @@
 #include "web_dev.cuh"
 
 #define DF_TX 32
-#define DF_TY 4
-#define DF_THREADS 128
 
 __constant__ double c_acoef[DKB_NS_MAX * DKB_NS_MAX];   // column-major (k,i) at [i*ns+k]
 __constant__ double c_bcoef[DKB_NS_MAX], c_cox[DKB_NS_MAX], c_coy[DKB_NS_MAX];
@@ -37,13 +35,14 @@ void datv_fused_upload_tables(const WebPar &p)
     cudaMemcpyToSymbol(c_coy, p.coy, sizeof(double) * p.ns);
 }
 
-template <int NS>
-__global__ void __launch_bounds__(DF_THREADS, 3)
+template <int NS, int DF_TY, int MINB>
+__global__ void __launch_bounds__(DF_TX * DF_TY, MINB)
 web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
                        const double *__restrict__ y, const double *__restrict__ ydot,
                        const double *__restrict__ savr, double cj, const double *__restrict__ lut,
                        const int *__restrict__ pt, double *__restrict__ vnext)
 {
+    constexpr int DF_THREADS = DF_TX * DF_TY;
     constexpr int ZX = DF_TX + 2, ZY = DF_TY + 2;
     constexpr int PZ = NS + 1;                 // pitch of a point's species in Z (odd: conflict-free)
     constexpr int NPH = NS / 2;                // differential species (prey) come first
@@ -58,7 +57,12 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
     const i64 mxns = (i64)w.mx * NS;
 
     // ---- phase 1: perturbed state for tile + halo (datv:3493-3498)
-    for (int idx = tid; idx < ZY * ZX * NS; idx += DF_THREADS) {
+    constexpr int NZ = ZY * ZX * NS;
+    constexpr int ITER1 = (NZ + DF_THREADS - 1) / DF_THREADS;
+#pragma unroll 8
+    for (int it = 0; it < ITER1; ++it) {
+        const int idx = tid + it * DF_THREADS;
+        if (idx >= NZ) break;
         const int zr = idx / (ZX * NS), rem = idx - zr * (ZX * NS);
         const int zx = rem / NS, i = rem - zx * NS;
         const int gy = y0 + zr - 1, gx = x0 + zx - 1;
@@ -163,20 +167,21 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
     }
 }
 
-template <int NS>
+template <int NS, int DF_TY, int MINB>
 static bool launch_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
                           const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
                           double *vnext)
 {
     static bool attr_set = false;
+    constexpr int DF_THREADS = DF_TX * DF_TY;
     constexpr int PZ = NS + 1, PY = (NS / 2) | 1;
     const size_t sh = sizeof(double) * ((DF_TX + 2) * (DF_TY + 2) * PZ + DF_THREADS * PY);
     if (!attr_set) {
-        cudaFuncSetAttribute(web_datv_single_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        cudaFuncSetAttribute(web_datv_single_kernel<NS, DF_TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         attr_set = true;
     }
     const int tiles = (w.mx / DF_TX) * ((w.my + DF_TY - 1) / DF_TY);
-    web_datv_single_kernel<NS><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    web_datv_single_kernel<NS, DF_TY, MINB><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
     g_ctx->launches++;
     return true;
 }
@@ -189,13 +194,19 @@ bool web_datv_single(const WebDev &w, const double *v, const double *wt, double 
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
     ProfScope ps(PROF_DATV1);
     switch (w.ns) {
-    case 2: return launch_single<2>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 4: return launch_single<4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 8: return launch_single<8>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 10: return launch_single<10>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 12: return launch_single<12>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 16: return launch_single<16>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 20: return launch_single<20>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 2: return launch_single<2, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 4: return launch_single<4, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 8: return launch_single<8, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 10: return launch_single<10, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 12: return launch_single<12, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 16: return launch_single<16, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 20:
+        switch (g_ctx->debug_variant) {
+        case 1: return launch_single<20, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        case 2: return launch_single<20, 8, 2>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        case 3: return launch_single<20, 2, 6>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        default: return launch_single<20, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        }
     default: return false;
     }
 }

@@ -52,6 +52,7 @@ struct DkbCtx {
     int opt_device_io = 0;
     int opt_fused = 2;           // 0: datv through the callbacks, 1: residual + solve kernels, 2: single fused kernel
     i64 opt_max_steps = 500;
+    int debug_variant = 0;       // kernel-variant selector for tuning runs (dkb_debug_*)
 
     // communicator (NCCL, loaded lazily)
     int rank = 0, nranks = 1;
