@@ -57,23 +57,41 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
     const i64 mxns = (i64)w.mx * NS;
 
     // ---- phase 1: perturbed state for tile + halo (datv:3493-3498)
+    // Loads are made unconditional (out-of-range cells read a safe in-tile address and are discarded)
+    // and issued U iterations at a time, so each thread has 4*U independent loads in flight instead
+    // of a load -> divide -> store chain per element.
     constexpr int NZ = ZY * ZX * NS;
     constexpr int ITER1 = (NZ + DF_THREADS - 1) / DF_THREADS;
-#pragma unroll 8
-    for (int it = 0; it < ITER1; ++it) {
-        const int idx = tid + it * DF_THREADS;
-        if (idx >= NZ) break;
-        const int zr = idx / (ZX * NS), rem = idx - zr * (ZX * NS);
-        const int zx = rem / NS, i = rem - zx * NS;
-        const int gy = y0 + zr - 1, gx = x0 + zx - 1;
-        const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
-        if (rowok && gx >= 0 && gx < w.mx) {
-            const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
-            const double wgt = wscale * __ldg(wt + g);
-            const double vtmp = __ldg(v + g) / wgt;                 // vtemp = v/wght
-            Z[(zr * ZX + zx) * PZ + i] = __ldg(y + g) + vtmp;       // z = y + vtemp
-            if (i < NPH && zr >= 1 && zr <= DF_TY && zx >= 1 && zx <= DF_TX && gy < w.my)
-                YDT[((zr - 1) * DF_TX + (zx - 1)) * PY + i] = __ldg(ydot + g) + vtmp * cj;   // ydottemp
+    constexpr int U = 8;
+    const i64 gsafe = (i64)y0 * mxns + (i64)x0 * NS;   // first unknown of the tile: always in range
+    for (int it0 = 0; it0 < ITER1; it0 += U) {
+        double rwt[U], rv[U], ry[U], ryd[U];
+        int zo[U], yo[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int idx = tid + (it0 + u) * DF_THREADS;
+            const int zr = idx / (ZX * NS), rem = idx - zr * (ZX * NS);
+            const int zx = rem / NS, i = rem - zx * NS;
+            const int gy = y0 + zr - 1, gx = x0 + zx - 1;
+            const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
+            const bool ok = (idx < NZ) && rowok && gx >= 0 && gx < w.mx;
+            const bool okyd = ok && i < NPH && zr >= 1 && zr <= DF_TY && zx >= 1 && zx <= DF_TX && gy < w.my;
+            const i64 g = ok ? ((i64)gy * mxns + (i64)gx * NS + i) : gsafe;
+            zo[u] = ok ? (zr * ZX + zx) * PZ + i : -1;
+            yo[u] = okyd ? ((zr - 1) * DF_TX + (zx - 1)) * PY + i : -1;
+            rwt[u] = __ldg(wt + g);
+            rv[u] = __ldg(v + g);
+            ry[u] = __ldg(y + g);
+            ryd[u] = __ldg(ydot + (okyd ? g : gsafe));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (zo[u] >= 0) {
+                const double wgt = wscale * rwt[u];
+                const double vtmp = rv[u] / wgt;               // vtemp = v/wght
+                Z[zo[u]] = ry[u] + vtmp;                       // z = y + vtemp
+                if (yo[u] >= 0) YDT[yo[u]] = ryd[u] + vtmp * cj;   // ydottemp = ydot + vtemp*cj
+            }
         }
     }
     __syncthreads();
@@ -155,14 +173,25 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
     }
     __syncthreads();
 
-    // ---- phase 3: z = z*wght (datv:3518), coalesced rows of 32*ns doubles
-    for (int idx = tid; idx < DF_THREADS * NS; idx += DF_THREADS) {
-        const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
-        const int oy = y0 + r;
-        if (oy < w.my) {
-            const i64 g = (i64)oy * mxns + (i64)x0 * NS + rem;
+    // ---- phase 3: z = z*wght (datv:3518), coalesced rows of 32*ns doubles; NS iterations per
+    // thread, weights loaded up front (unconditionally, clamped) so the loads overlap
+    {
+        double rw[NS];
+        i64 go[NS];
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            const int idx = tid + m * DF_THREADS;
+            const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
+            const int oy = y0 + r;
+            go[m] = (oy < w.my) ? ((i64)oy * mxns + (i64)x0 * NS + rem) : -1;
+            rw[m] = __ldg(wt + (go[m] >= 0 ? go[m] : gsafe));
+        }
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            const int idx = tid + m * DF_THREADS;
+            const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
             const int q = r * DF_TX + rem / NS;
-            vnext[g] = Z[q * PZ + (rem % NS)] * (wscale * __ldg(wt + g));
+            if (go[m] >= 0) vnext[go[m]] = Z[q * PZ + (rem % NS)] * (wscale * rw[m]);
         }
     }
 }
@@ -194,18 +223,17 @@ bool web_datv_single(const WebDev &w, const double *v, const double *wt, double 
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
     ProfScope ps(PROF_DATV1);
     switch (w.ns) {
-    case 2: return launch_single<2, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 4: return launch_single<4, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 8: return launch_single<8, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 10: return launch_single<10, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 12: return launch_single<12, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 16: return launch_single<16, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 2: return launch_single<2, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 4: return launch_single<4, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 8: return launch_single<8, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 10: return launch_single<10, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 12: return launch_single<12, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 16: return launch_single<16, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
     case 20:
         switch (g_ctx->debug_variant) {
-        case 1: return launch_single<20, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        case 1: return launch_single<20, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
         case 2: return launch_single<20, 8, 2>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-        case 3: return launch_single<20, 2, 6>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-        default: return launch_single<20, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        default: return launch_single<20, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);   // 128 regs, 16 warps/SM: fastest measured
         }
     default: return false;
     }
