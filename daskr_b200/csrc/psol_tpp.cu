@@ -41,14 +41,24 @@ tpp_psol_kernel(const double *__restrict__ lut, const int *__restrict__ pt, i64 
         const i64 p0 = tile * TPP_THREADS;
         const i64 g0 = p0 * NS;
         const i64 nval = min((i64)TPP_THREADS, npts - p0) * NS;
-        // ---- phase 1: coalesced load of the tile's right-hand sides, (vtemp - savr) of datv:3509
-        for (int idx = tid; idx < TPP_THREADS * NS; idx += TPP_THREADS) {
-            double x = 0.0;
-            if (idx < nval) {
-                x = in[g0 + idx];
-                if (savr) x = x - savr[g0 + idx];
+        // ---- phase 1: coalesced load of the tile's right-hand sides, (vtemp - savr) of datv:3509.
+        // Unconditional (clamped) loads, all NS per thread issued before the first use.
+        {
+            double rin[NS], rsv[NS];
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+                const int idx = tid + m * TPP_THREADS;
+                const i64 g = g0 + (idx < nval ? idx : 0);
+                rin[m] = in[g];
+                rsv[m] = savr ? savr[g] : 0.0;
             }
-            sb[(idx / NS) * PITCH + (idx % NS)] = x;
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+                const int idx = tid + m * TPP_THREADS;
+                double x = 0.0;
+                if (idx < nval) x = savr ? (rin[m] - rsv[m]) : rin[m];
+                sb[(idx / NS) * PITCH + (idx % NS)] = x;
+            }
         }
         __syncthreads();
 
@@ -97,12 +107,22 @@ tpp_psol_kernel(const double *__restrict__ lut, const int *__restrict__ pt, i64 
         __syncthreads();
 
         // ---- phase 3: coalesced store, z = z*wght (datv:3518 / dspigm:3281) and the norm partial
-        for (int idx = tid; idx < TPP_THREADS * NS; idx += TPP_THREADS) {
-            if (idx < nval) {
-                double x = sb[(idx / NS) * PITCH + (idx % NS)];
-                if (wt) x = x * (wscale * wt[g0 + idx]);
-                out[g0 + idx] = x;
-                acc = acc + x * x;
+        {
+            double rw[NS];
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+                const int idx = tid + m * TPP_THREADS;
+                rw[m] = wt ? wt[g0 + (idx < nval ? idx : 0)] : 1.0;
+            }
+#pragma unroll
+            for (int m = 0; m < NS; ++m) {
+                const int idx = tid + m * TPP_THREADS;
+                if (idx < nval) {
+                    double x = sb[(idx / NS) * PITCH + (idx % NS)];
+                    if (wt) x = x * (wscale * rw[m]);
+                    out[g0 + idx] = x;
+                    acc = acc + x * x;
+                }
             }
         }
         __syncthreads();

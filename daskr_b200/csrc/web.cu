@@ -114,27 +114,39 @@ web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restr
     const int gx = x0 + x;
     const i64 mxns = (i64)w.mx * NS;
 
-    // ---- phase 1a: this thread's own unknowns, one per tile row (kept in registers across the barrier)
+    // ---- phase 1a: this thread's own unknowns, one per tile row (kept in registers across the barrier).
+    // Loads are unconditional (cells outside the slab read a safe in-tile address and are discarded)
+    // so that all of them are in flight before the first divide.
     double ydt[RT_TY];
+    {
+        double rw[RT_TY], rv[RT_TY], ryy[RT_TY];
+        const i64 gsafe = (i64)y0 * mxns + (i64)x0 * NS;
 #pragma unroll
-    for (int ry = 0; ry < RT_TY; ++ry) {
-        const int gy = y0 + ry;
-        ydt[ry] = 0.0;
-        // rows of the tile beyond the slab: the first one is the upper neighbour's ghost row and is
-        // needed by the last local row when the slab height is not a multiple of the tile height
-        if ((gy < w.my || (gy == w.my && w.has_hi)) && gx < w.mx) {
-            const i64 g = (i64)gy * mxns + (i64)gx * NS + i;
-            double z;
+        for (int ry = 0; ry < RT_TY; ++ry) {
+            const int gy = y0 + ry;
+            // rows of the tile beyond the slab: the first one is the upper neighbour's ghost row and
+            // is needed by the last local row when the slab height is not a multiple of the tile height
+            const bool ok = (gy < w.my || (gy == w.my && w.has_hi)) && gx < w.mx;
+            const i64 g = ok ? ((i64)gy * mxns + (i64)gx * NS + i) : gsafe;
+            ryy[ry] = __ldg(y + g);
+            ydt[ry] = __ldg(ydot + g);
             if (DATV) {
-                const double wgt = wscale * __ldg(wt + g);
-                const double vtmp = __ldg(v + g) / wgt;        // vtemp = v/wght            (datv:3493)
-                z = __ldg(y + g) + vtmp;                       // z = y + vtemp             (:3498)
-                ydt[ry] = __ldg(ydot + g) + vtmp * cj;         // ydottemp = ydot + vtemp*cj (:3497)
-            } else {
-                z = __ldg(y + g);
-                ydt[ry] = __ldg(ydot + g);
+                rw[ry] = __ldg(wt + g);
+                rv[ry] = __ldg(v + g);
             }
-            Z[((ry + 1) * ZX + (x + 1)) * NS + i] = z;
+        }
+#pragma unroll
+        for (int ry = 0; ry < RT_TY; ++ry) {
+            const int gy = y0 + ry;
+            const bool ok = (gy < w.my || (gy == w.my && w.has_hi)) && gx < w.mx;
+            double z = ryy[ry];
+            if (DATV) {
+                const double wgt = wscale * rw[ry];
+                const double vtmp = rv[ry] / wgt;              // vtemp = v/wght            (datv:3493)
+                z = ryy[ry] + vtmp;                            // z = y + vtemp             (:3498)
+                ydt[ry] = ydt[ry] + vtmp * cj;                 // ydottemp = ydot + vtemp*cj (:3497)
+            }
+            if (ok) Z[((ry + 1) * ZX + (x + 1)) * NS + i] = z;
         }
     }
     // ---- phase 1b: the stencil halo of the tile (no corners)
