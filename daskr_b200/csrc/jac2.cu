@@ -1,0 +1,147 @@
+// jac2.cu -- K5: jac_rbdpre (src/daskr_rbdpre.f90:158-251) for the food-web problem in two phases
+// inside one kernel, so that each phase can use the mapping that suits it:
+//
+//   phase FD (thread per (mesh point, block row), all 32 lanes of every warp busy):
+//       bd(k,js) = -(R_k(u + del_js e_js) - R_k(u))/del_js, + cj on the first nsd diagonals,
+//       with the point's concentrations, del and -1/del staged in shared memory and this thread's
+//       row of acoef in registers.  The unfactored ns x ns blocks of the CTA's points land in shared
+//       memory (rows conflict-free on write, columns conflict-free on read).
+//   phase LU (one sub-warp group per point, lane = row): LINPACK dgefa with logical row
+//       interchanges (group_dgefa_track, lu_device.cuh); every finished column goes straight to
+//       the tile-interleaved global layout of psol_tpp.cu at its LINPACK position.
+//
+// The earlier single-mapping kernel (lane = row for both phases) ran the FD part on 20 of 32 lanes
+// with 230 registers per thread (8 warps/SM): 10 ms per call at 1024^2 x 20.  Arithmetic is
+// unchanged (reference operation order, no FMA), so blocks and pivots stay bit-identical to the
+// CPU path.
+#include "web_dev.cuh"
+#include "lu_device.cuh"
+
+template <int NS> struct J2 {
+    static constexpr int PTS = NS >= 16 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;   // points per CTA
+    static constexpr int THREADS = NS * PTS;
+};
+
+template <int NS>
+__global__ void __launch_bounds__(J2<NS>::THREADS)
+web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *__restrict__ rewt, double cj,
+                double *__restrict__ bd, int *__restrict__ ipbd, int *first_flag)
+{
+    constexpr int PTS = J2<NS>::PTS, THREADS = J2<NS>::THREADS;
+    constexpr int G = GroupOf<NS>::G;
+    constexpr int NSQ = NS * NS;
+    extern __shared__ double sm[];
+    double *blk = sm;                       // [PTS][NSQ]   column-major blocks
+    double *sc = blk + PTS * NSQ;           // [PTS][NS]    concentrations
+    double *sdel = sc + PTS * NS;           // [PTS][NS]    del_j
+    double *sfd = sdel + PTS * NS;          // [PTS][NS]    -1/del_j
+    const int tid = threadIdx.x;
+    const i64 npts = (i64)w.mx * w.my;
+    const i64 p0 = (i64)blockIdx.x * PTS;
+
+    // ---------------- phase FD
+    {
+        const int pl = tid / NS, k = tid - pl * NS;
+        const i64 p = p0 + pl;
+        const bool live = p < npts;
+        const i64 idx = (live ? p : npts - 1) * NS + k;
+        const double ci = __ldg(c + idx);
+        const double rw = __ldg(rewt + idx);
+        double arow[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) arow[j] = __ldg(w.acoef + j * NS + k);
+        const double bco = __ldg(w.bcoef + k);
+        const double del = fmax(w.srur * fabs(ci), 1e-2 / rw);   // jac_rbdpre:222
+        sc[pl * NS + k] = ci;
+        sdel[pl * NS + k] = del;
+        sfd[pl * NS + k] = -1.0 / del;                            // fac = -one/del (:224)
+        __syncthreads();
+        const i64 pp = live ? p : npts - 1;
+        const int jyl = (int)(pp / w.mx);
+        const int jx = (int)(pp - (i64)jyl * w.mx);
+        const int jyg = w.jy0 + jyl;
+        const double yy = jyg * w.dy, xx = jx * w.dx;
+        const double fac = 1.0 + w.alpha * xx * yy + w.beta * __ldg(w.sx + jx) * __ldg(w.sy + jyg);
+        const double *cp = sc + pl * NS;
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) r = r + cp[j] * arow[j];
+        const double r0 = ci * (bco * fac + r);                   // what res left in rpar (f:250)
+        double *bp = blk + pl * NSQ;
+#pragma unroll
+        for (int js = 0; js < NS; ++js) {
+            const double up = cp[js] + sdel[pl * NS + js];        // u(j) = u(j) + del (:223)
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s = s + ((j == js) ? up : cp[j]) * arow[j];
+            const double cown = (k == js) ? up : ci;
+            const double r1 = cown * (bco * fac + s);
+            double val = (r1 - r0) * sfd[pl * NS + js];           // (:226-228)
+            if (k == js && k < nsd) val = val + cj;               // + cj*I_d (:240-244)
+            bp[js * NS + k] = val;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase LU
+    {
+        const int li = tid % G, gid = tid / G;
+        constexpr int NGRP = THREADS / G;
+        constexpr int ROUNDS = (PTS + NGRP - 1) / NGRP;
+#pragma unroll 1
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+            const int pl = gid + rd * NGRP;
+            const i64 p = p0 + pl;
+            const bool live = (pl < PTS) && (p < npts);
+            const int plc = pl < PTS ? pl : PTS - 1;
+            double a[NS];
+#pragma unroll
+            for (int j = 0; j < NS; ++j) a[j] = (li < NS) ? blk[plc * NSQ + j * NS + li] : 0.0;
+            const i64 pq = live ? p : 0;
+            double *gb = bd + ((pq >> 5) * NSQ) * 32 + (pq & 31);
+            int ipv;
+            const int inf = group_dgefa_track<NS>(a, li, ipv, [&](int col, int pos, double val) {
+                if (live && li < NS) gb[(col * NS + pos) * 32] = val;
+            });
+            if (live && li < NS) {
+                ipbd[((p >> 5) * NS + li) * 32 + (p & 31)] = ipv;
+                if (li == 0 && inf != 0) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
+            }
+        }
+    }
+}
+
+template <int NS>
+static void jac2_launch(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd,
+                        int *ipbd, int *d_first_flag)
+{
+    static bool attr_set = false;
+    constexpr int PTS = J2<NS>::PTS;
+    const size_t sh = sizeof(double) * (PTS * NS * NS + 3 * PTS * NS);
+    if (!attr_set) {
+        cudaFuncSetAttribute(web_jac2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        attr_set = true;
+    }
+    const i64 npts = (i64)w.mx * w.my;
+    const int grid = (int)((npts + PTS - 1) / PTS);
+    web_jac2_kernel<NS><<<grid, J2<NS>::THREADS, sh, g_ctx->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag);
+    g_ctx->launches++;
+}
+
+bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
+              int *d_first_flag)
+{
+    switch (w.ns) {
+    case 2: jac2_launch<2>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 4: jac2_launch<4>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 6: jac2_launch<6>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 8: jac2_launch<8>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 10: jac2_launch<10>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 12: jac2_launch<12>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 16: jac2_launch<16>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 20: jac2_launch<20>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 24: jac2_launch<24>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 32: jac2_launch<32>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    default: return false;
+    }
+}

@@ -331,6 +331,7 @@ void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, 
     WebDev w = make_webdev();
     const i64 npts = x->npts;
     const int nsd = x->nsd;
+    if (x->debug_variant != 9 && web_jac2(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)) return;   // two-phase kernel (jac2.cu)
 #define CALL(N) web_jac_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 128, 8), 128, 0, x->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL

@@ -12,6 +12,9 @@ struct WebDev {
 WebDev make_webdev();
 // copies acoef / bcoef / cox / coy into the constant bank the fused datv kernel reads them from
 void datv_fused_upload_tables(const WebPar &p);
+// two-phase FD + LU block Jacobian (jac2.cu)
+bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
+              int *d_first_flag);
 // single-kernel datv; returns false if the mesh / ns is not eligible (caller falls back)
 bool web_datv_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
                      const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
