@@ -18,7 +18,9 @@
 #include "lu_device.cuh"
 
 template <int NS> struct J2 {
-    static constexpr int PTS = NS >= 16 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;   // points per CTA
+    // points per CTA: as many as shared memory (PTS*NS*NS doubles) and 1024 threads allow, so that the
+    // LU phase has a block for (almost) every warp in each of its rounds
+    static constexpr int PTS = NS > 20 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;
     static constexpr int THREADS = NS * PTS;
 };
 

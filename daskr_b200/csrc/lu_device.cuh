@@ -99,6 +99,10 @@ __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &i
 #pragma unroll
     for (int k = 0; k < NS - 1; ++k) {
         const bool cand = (li < NS) && (r >= k);
+        // every lane forms -1/a(i,k) for its own row while the pivot search runs; the pivot row's
+        // value (== -1/a(k,k) after the interchange, linpack.f90:409) is broadcast afterwards, which
+        // takes the divide latency off the critical path of the step
+        const double tcand = -1.0 / a[k];
         const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(fabs(a[k])) : 0ull;
         const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
         const unsigned mhi = __reduce_max_sync(mask, hi);
@@ -115,7 +119,7 @@ __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &i
         }
         if (r == (int)l) r = k;
         else if (r == k) r = (int)l;
-        const double t = -1.0 / piv;
+        const double t = shfl_d(mask, tcand, pl, G);
         if (r > k) a[k] = a[k] * t;   // multipliers (negated)
         store(k, r, a[k]);
 #pragma unroll
