@@ -742,6 +742,31 @@ int dkb_debug_time_datv(int level, int variant, int reps, double *ms)
     return 0;
 }
 
+int dkb_debug_time_jac(int variant, int reps, double *ms)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena || c->problem != DKB_PROB_WEB) return dkb_fail(DKB_E_STATE, "needs a food-web solver state");
+    const int save_v = c->debug_variant;
+    c->debug_variant = variant;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    arm_first_flag(c);
+    web_jac_launch(c->y, c->wt, 1.0e4, c->wp, c->iwp, c->d_iflag + 1);
+    cudaEventRecord(a, c->stream);
+    for (int i = 0; i < reps; ++i) web_jac_launch(c->y, c->wt, 1.0e4, c->wp, c->iwp, c->d_iflag + 1);
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, a, b);
+    *ms = t / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    c->debug_variant = save_v;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------- measurement hooks
 int dkb_prof_enable(int on)
 {

@@ -18,18 +18,15 @@
 #include "lu_device.cuh"
 
 template <int NS> struct J2 {
-    // points per CTA: as many as shared memory (PTS*NS*NS doubles) and 1024 threads allow, so that the
-    // LU phase has a block for (almost) every warp in each of its rounds
-    static constexpr int PTS = NS > 20 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;
-    static constexpr int THREADS = NS * PTS;
+    static constexpr int PTS = NS >= 16 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;   // default points per CTA
 };
 
-template <int NS>
-__global__ void __launch_bounds__(J2<NS>::THREADS)
+template <int NS, int PTS, bool SPEC>
+__global__ void __launch_bounds__(NS * PTS)
 web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *__restrict__ rewt, double cj,
                 double *__restrict__ bd, int *__restrict__ ipbd, int *first_flag)
 {
-    constexpr int PTS = J2<NS>::PTS, THREADS = J2<NS>::THREADS;
+    constexpr int THREADS = NS * PTS;
     constexpr int G = GroupOf<NS>::G;
     constexpr int NSQ = NS * NS;
     extern __shared__ double sm[];
@@ -102,7 +99,7 @@ web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
             const i64 pq = live ? p : 0;
             double *gb = bd + ((pq >> 5) * NSQ) * 32 + (pq & 31);
             int ipv;
-            const int inf = group_dgefa_track<NS>(a, li, ipv, [&](int col, int pos, double val) {
+            const int inf = group_dgefa_track<NS, SPEC>(a, li, ipv, [&](int col, int pos, double val) {
                 if (live && li < NS) gb[(col * NS + pos) * 32] = val;
             });
             if (live && li < NS) {
@@ -113,20 +110,19 @@ web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
     }
 }
 
-template <int NS>
+template <int NS, int PTS = J2<NS>::PTS, bool SPEC = false>
 static void jac2_launch(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd,
                         int *ipbd, int *d_first_flag)
 {
     static bool attr_set = false;
-    constexpr int PTS = J2<NS>::PTS;
     const size_t sh = sizeof(double) * (PTS * NS * NS + 3 * PTS * NS);
     if (!attr_set) {
-        cudaFuncSetAttribute(web_jac2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        cudaFuncSetAttribute(web_jac2_kernel<NS, PTS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         attr_set = true;
     }
     const i64 npts = (i64)w.mx * w.my;
     const int grid = (int)((npts + PTS - 1) / PTS);
-    web_jac2_kernel<NS><<<grid, J2<NS>::THREADS, sh, g_ctx->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag);
+    web_jac2_kernel<NS, PTS, SPEC><<<grid, NS * PTS, sh, g_ctx->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag);
     g_ctx->launches++;
 }
 
@@ -141,7 +137,16 @@ bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, dou
     case 10: jac2_launch<10>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     case 12: jac2_launch<12>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     case 16: jac2_launch<16>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
-    case 20: jac2_launch<20>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
+    case 20:
+        switch (g_ctx->debug_variant) {
+        case 1: jac2_launch<20, 16, true>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        case 2: jac2_launch<20, 32, false>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        case 3: jac2_launch<20, 32, true>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        case 4: jac2_launch<20, 8, false>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        case 5: jac2_launch<20, 8, true>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        default: jac2_launch<20, 16, false>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
+        }
+        return true;
     case 24: jac2_launch<24>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     case 32: jac2_launch<32>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     default: return false;

@@ -87,7 +87,7 @@ __device__ __forceinline__ int group_dgefa(double (&a)[NS], int li, int &ipv)
 // (idamax: first maximum) runs on the integer image of |a| with three warp reductions instead of a
 // five-round shuffle butterfly.  Column k is final once step k is done; `store(col, pos, value)`
 // is called for every lane with pos = the row LINPACK would hold that value in.
-template <int NS, class Store>
+template <int NS, bool SPEC = true, class Store>
 __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &ipv, Store store)
 {
     constexpr int G = GroupOf<NS>::G;
@@ -102,7 +102,7 @@ __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &i
         // every lane forms -1/a(i,k) for its own row while the pivot search runs; the pivot row's
         // value (== -1/a(k,k) after the interchange, linpack.f90:409) is broadcast afterwards, which
         // takes the divide latency off the critical path of the step
-        const double tcand = -1.0 / a[k];
+        const double tcand = SPEC ? -1.0 / a[k] : 0.0;
         const unsigned long long key = cand ? (unsigned long long)__double_as_longlong(fabs(a[k])) : 0ull;
         const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
         const unsigned mhi = __reduce_max_sync(mask, hi);
@@ -119,7 +119,7 @@ __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &i
         }
         if (r == (int)l) r = k;
         else if (r == k) r = (int)l;
-        const double t = shfl_d(mask, tcand, pl, G);
+        const double t = SPEC ? shfl_d(mask, tcand, pl, G) : -1.0 / piv;
         if (r > k) a[k] = a[k] * t;   // multipliers (negated)
         store(k, r, a[k]);
 #pragma unroll
