@@ -21,6 +21,15 @@ template <int NS> struct J2 {
     static constexpr int PTS = NS >= 16 ? 16 : NS >= 8 ? 32 : NS >= 4 ? 64 : 128;   // default points per CTA
 };
 
+__constant__ double j_acoef[DKB_NS_MAX * DKB_NS_MAX];   // column-major (k,j) at [j*ns+k]
+__constant__ double j_bcoef[DKB_NS_MAX];
+
+void jac2_upload_tables(const WebPar &p)
+{
+    cudaMemcpyToSymbol(j_acoef, p.acoef, sizeof(double) * p.ns * p.ns);
+    cudaMemcpyToSymbol(j_bcoef, p.bcoef, sizeof(double) * p.ns);
+}
+
 template <int NS, int PTS, bool SPEC>
 __global__ void __launch_bounds__(NS * PTS)
 web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *__restrict__ rewt, double cj,
@@ -29,55 +38,59 @@ web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
     constexpr int THREADS = NS * PTS;
     constexpr int G = GroupOf<NS>::G;
     constexpr int NSQ = NS * NS;
+    constexpr int CP = NS + 1;              // column pitch in shared memory (odd: columns written by
+    constexpr int BP = NS * CP;             // neighbouring threads fall into different banks)
     extern __shared__ double sm[];
-    double *blk = sm;                       // [PTS][NSQ]   column-major blocks
-    double *sc = blk + PTS * NSQ;           // [PTS][NS]    concentrations
-    double *sdel = sc + PTS * NS;           // [PTS][NS]    del_j
-    double *sfd = sdel + PTS * NS;          // [PTS][NS]    -1/del_j
+    double *blk = sm;                       // [PTS][NS columns][CP]
+    double *sc = blk + PTS * BP;            // [PTS][NS]    concentrations
+    double *sr0 = sc + PTS * NS;            // [PTS][NS]    R(u), what res left in rpar (f:250)
     const int tid = threadIdx.x;
     const i64 npts = (i64)w.mx * w.my;
     const i64 p0 = (i64)blockIdx.x * PTS;
 
-    // ---------------- phase FD
+    // ---------------- phase FD: thread (point pl, column js) -- one perturbation per thread
     {
-        const int pl = tid / NS, k = tid - pl * NS;
+        const int pl = tid / NS, js = tid - pl * NS;
         const i64 p = p0 + pl;
-        const bool live = p < npts;
-        const i64 idx = (live ? p : npts - 1) * NS + k;
-        const double ci = __ldg(c + idx);
+        const i64 pp = p < npts ? p : npts - 1;
+        const i64 idx = pp * NS + js;
+        const double cjs = __ldg(c + idx);
         const double rw = __ldg(rewt + idx);
-        double arow[NS];
-#pragma unroll
-        for (int j = 0; j < NS; ++j) arow[j] = __ldg(w.acoef + j * NS + k);
-        const double bco = __ldg(w.bcoef + k);
-        const double del = fmax(w.srur * fabs(ci), 1e-2 / rw);   // jac_rbdpre:222
-        sc[pl * NS + k] = ci;
-        sdel[pl * NS + k] = del;
-        sfd[pl * NS + k] = -1.0 / del;                            // fac = -one/del (:224)
+        sc[pl * NS + js] = cjs;
         __syncthreads();
-        const i64 pp = live ? p : npts - 1;
+        double cb[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) cb[j] = sc[pl * NS + j];
         const int jyl = (int)(pp / w.mx);
         const int jx = (int)(pp - (i64)jyl * w.mx);
         const int jyg = w.jy0 + jyl;
         const double yy = jyg * w.dy, xx = jx * w.dx;
         const double fac = 1.0 + w.alpha * xx * yy + w.beta * __ldg(w.sx + jx) * __ldg(w.sy + jyg);
-        const double *cp = sc + pl * NS;
-        double r = 0.0;
+        // R_js(u) by this thread (rates:290-297 for row js), shared with the point's other threads
+        {
+            double r = 0.0;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) r = r + cp[j] * arow[j];
-        const double r0 = ci * (bco * fac + r);                   // what res left in rpar (f:250)
-        double *bp = blk + pl * NSQ;
+            for (int j = 0; j < NS; ++j) r = r + cb[j] * __ldg(w.acoef + j * NS + js);
+            sr0[pl * NS + js] = cjs * (__ldg(w.bcoef + js) * fac + r);
+        }
+        const double del = fmax(w.srur * fabs(cjs), 1e-2 / rw);   // jac_rbdpre:222
+        const double up = cjs + del;                              // u(j) = u(j) + del  (:223)
+        const double fd = -1.0 / del;                             // fac = -one/del     (:224)
 #pragma unroll
-        for (int js = 0; js < NS; ++js) {
-            const double up = cp[js] + sdel[pl * NS + js];        // u(j) = u(j) + del (:223)
+        for (int j = 0; j < NS; ++j)
+            if (j == js) cb[j] = up;                              // the perturbed point state
+        __syncthreads();
+        double *bp = blk + pl * BP + js * CP;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            // rblock at the perturbed state, row k (acoef is a uniform constant-bank operand here)
             double s = 0.0;
 #pragma unroll
-            for (int j = 0; j < NS; ++j) s = s + ((j == js) ? up : cp[j]) * arow[j];
-            const double cown = (k == js) ? up : ci;
-            const double r1 = cown * (bco * fac + s);
-            double val = (r1 - r0) * sfd[pl * NS + js];           // (:226-228)
+            for (int j = 0; j < NS; ++j) s = s + cb[j] * j_acoef[j * NS + k];
+            const double r1 = cb[k] * (j_bcoef[k] * fac + s);
+            double val = (r1 - sr0[pl * NS + k]) * fd;            // (:226-228)
             if (k == js && k < nsd) val = val + cj;               // + cj*I_d (:240-244)
-            bp[js * NS + k] = val;
+            bp[k] = val;
         }
     }
     __syncthreads();
@@ -95,7 +108,7 @@ web_jac2_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
             const int plc = pl < PTS ? pl : PTS - 1;
             double a[NS];
 #pragma unroll
-            for (int j = 0; j < NS; ++j) a[j] = (li < NS) ? blk[plc * NSQ + j * NS + li] : 0.0;
+            for (int j = 0; j < NS; ++j) a[j] = (li < NS) ? blk[plc * BP + j * CP + li] : 0.0;
             const i64 pq = live ? p : 0;
             double *gb = bd + ((pq >> 5) * NSQ) * 32 + (pq & 31);
             int ipv;
@@ -115,7 +128,7 @@ static void jac2_launch(const WebDev &w, int nsd, const double *c, const double 
                         int *ipbd, int *d_first_flag)
 {
     static bool attr_set = false;
-    const size_t sh = sizeof(double) * (PTS * NS * NS + 3 * PTS * NS);
+    const size_t sh = sizeof(double) * (PTS * NS * (NS + 1) + 2 * PTS * NS);
     if (!attr_set) {
         cudaFuncSetAttribute(web_jac2_kernel<NS, PTS, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         attr_set = true;

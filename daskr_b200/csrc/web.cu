@@ -71,6 +71,7 @@ void web_upload_tables()
     cudaMalloc(&c->d_sx, tab.size() * sizeof(double));
     cudaMemcpy(c->d_sx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
     datv_fused_upload_tables(p);
+    jac2_upload_tables(p);
     dkb_cuda_check("web_upload_tables");
 }
 

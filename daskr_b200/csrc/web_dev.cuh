@@ -12,6 +12,7 @@ struct WebDev {
 WebDev make_webdev();
 // copies acoef / bcoef / cox / coy into the constant bank the fused datv kernel reads them from
 void datv_fused_upload_tables(const WebPar &p);
+void jac2_upload_tables(const WebPar &p);
 // two-phase FD + LU block Jacobian (jac2.cu)
 bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
               int *d_first_flag);
