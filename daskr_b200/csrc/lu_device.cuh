@@ -120,12 +120,17 @@ __device__ __forceinline__ int group_dgefa_track(double (&a)[NS], int li, int &i
         if (r == (int)l) r = k;
         else if (r == k) r = (int)l;
         const double t = SPEC ? shfl_d(mask, tcand, pl, G) : -1.0 / piv;
-        if (r > k) a[k] = a[k] * t;   // multipliers (negated)
+        const bool below = r > k;           // rows still to be eliminated in this step
+        if (below) a[k] = a[k] * t;         // multipliers (negated)
         store(k, r, a[k]);
+        // broadcast the pivot row's tail first (all lanes), then one divergent region of straight-line
+        // multiply-adds for the rows below the pivot: no per-element selects
+        double tj[NS];
 #pragma unroll
-        for (int j = k + 1; j < NS; ++j) {
-            const double tj = shfl_d(mask, a[j], pl, G);
-            if (r > k) a[j] = a[j] + tj * a[k];
+        for (int j = k + 1; j < NS; ++j) tj[j] = shfl_d(mask, a[j], pl, G);
+        if (below) {
+#pragma unroll
+            for (int j = k + 1; j < NS; ++j) a[j] = a[j] + tj[j] * a[k];
         }
     }
     store(NS - 1, r, a[NS - 1]);
