@@ -64,7 +64,8 @@ def test_web_1024_ns20_paths_agree(dk):
     assert np.array_equal(runs[2]["counters"], runs[1]["counters"])
     y = runs[2]["y"][-1].reshape(1024, 1024, 20)
     assert np.isfinite(y).all()
-    assert y[:, :, :10].min() > 9.0 and y[:, :, 10:].min() > 0.0   # prey >= 10-ish, predators positive
+    pmin, qmin = y[:, :, :10].min(), y[:, :, 10:].min()
+    assert pmin > 9.0 and qmin > 0.0, (pmin, qmin)                 # prey >= 10-ish, predators positive
     cnt = runs[2]["counters"][-1]
     assert cnt[10] == 6 and cnt[14] == 0 and cnt[15] == 0           # 6 steps, no convergence failures
     # symmetry property of the problem: the initial profile and the rate factor are symmetric under
