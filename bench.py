@@ -211,7 +211,7 @@ def run_ours(args):
     c_t = torch.empty(neq, dtype=torch.float64).pin_memory()
     cd_t = torch.empty(neq, dtype=torch.float64).pin_memory()
     c, cdot = c_t.numpy(), cd_t.numpy()
-    c0, cdot0 = dk.web_cinit(neq)
+    c0, cdot0 = dk.web_cinit(neq, 1e5 * NP_SPECIES)   # predator guess ee*10*np (example: 1e5 at np=1)
     c[:] = c0
     cdot[:] = cdot0
     del c0, cdot0

@@ -306,7 +306,7 @@ def launch_count():
 
 
 # ---------------------------------------------------------------- whole-run drivers
-def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fused=True, ic=True, pred_ic=1e5,
+def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fused=True, ic=True, pred_ic=None,
               y_out=True):
     """The food-web example as example/example_web.f90:884-954 runs it (Krylov, no grouping, nrt=0):
     one DASKR call for consistent initial values (info(11)=1, info(14)=1 -> idid=4), then integration
@@ -329,6 +329,8 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     rwork = np.zeros(60)
     rpar = np.zeros(1)
     ipar = np.array([jpre, 0], dtype=np.int32)
+    if pred_ic is None:
+        pred_ic = 1e5 * np_   # example_web.f90:784 uses 1e5 for np=1 (= ee * prey level * np): start near the non-trivial branch
     c, cdot = web_cinit(neq, pred_ic)
     t = 0.0
     idid = 0

@@ -1376,7 +1376,9 @@ int o_run_web(int np, int mx, int my, int jpre, double rtol_, double atol_,
     double t = 0.0, tout = touts[0];
     int idid = 0, nrt = 0, jroot = 0;
 
-    o_web_cinit(c.data(), cdot.data(), 1e5, rpar.data());
+    /* flat predator guess: the example uses 1e5 for np = 1 (example_web.f90:784), i.e. ee * (prey level 10) * np;
+       scaled with np so that Newton starts near the non-trivial predator branch for np > 1 as well */
+    o_web_cinit(c.data(), cdot.data(), 1e5 * np, rpar.data());
 
     /* initial-condition call */
     o_daskr(o_web_res, &neq32, &t, c.data(), cdot.data(), &tout, info, &rtol, &atol, &idid,

@@ -65,7 +65,7 @@ def test_web_1024_ns20_paths_agree(dk):
     y = runs[2]["y"][-1].reshape(1024, 1024, 20)
     assert np.isfinite(y).all()
     pmin, qmin = y[:, :, :10].min(), y[:, :, 10:].min()
-    assert pmin > 9.0 and qmin > 0.0, (pmin, qmin)                 # prey >= 10-ish, predators positive
+    assert pmin > 1.0 and qmin > 1e4, (pmin, qmin)                 # prey positive, predators on the non-trivial branch
     cnt = runs[2]["counters"][-1]
     assert cnt[10] == 6 and cnt[14] == 0 and cnt[15] == 0           # 6 steps, no convergence failures
     # symmetry property of the problem: the initial profile and the rate factor are symmetric under
