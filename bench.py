@@ -178,9 +178,22 @@ def run_ours(args):
     dk.init(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("DKB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dk.comm_init_from_torch(rank, world)
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at any debug level
+        os.environ.pop("NCCL_DEBUG", None)
+        if "DKB_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["DKB_NCCL_DEBUG"]
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)   # anything the communicator set-up prints goes to stderr
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dk.comm_init_from_torch(rank, world)
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     K, W = args.steps, args.warmup
     ns = 2 * NP_SPECIES
