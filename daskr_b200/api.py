@@ -34,7 +34,7 @@ EXPORTS = [
     "dkb_heat_psol", "dkb_heat_uinit", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
-    "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
+    "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
 ]
 
 
@@ -63,6 +63,7 @@ def lib():
     L.dkb_free.argtypes = [C.c_void_p]
     L.dkb_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.dkb_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.dkb_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.dkb_memset.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     L.dkb_comm_unique_id.argtypes = [C.c_void_p]
     L.dkb_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -705,6 +705,13 @@ int dkb_memcpy_d2h(void *dst, const void *src, int64_t bytes)
     CUDA_TRY(cudaStreamSynchronize(g_ctx->stream));
     return 0;
 }
+int dkb_memcpy_d2d(void *dst, const void *src, int64_t bytes)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, g_ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx->stream));
+    return 0;
+}
 int dkb_memset(void *dst, int value, int64_t bytes)
 {
     if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");

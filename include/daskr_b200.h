@@ -172,6 +172,7 @@ int dkb_malloc(void **ptr, int64_t bytes);
 int dkb_free(void *ptr);
 int dkb_memcpy_h2d(void *dst, const void *src, int64_t bytes);
 int dkb_memcpy_d2h(void *dst, const void *src, int64_t bytes);
+int dkb_memcpy_d2d(void *dst, const void *src, int64_t bytes);
 int dkb_memset(void *dst, int value, int64_t bytes);
 
 /* ---- measurement hooks (bench.py): kernel-time accumulation by CUDA events ---- */
