@@ -13,6 +13,7 @@
 #include "dkb_internal.h"
 
 #include "lu_device.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------ kernels
 template <int NS>
@@ -30,17 +31,68 @@ __global__ void __launch_bounds__(256) dgefa_kernel(double *bd, int *ipbd, i64 n
         double *blk = bd + p * (NS * NS);
         double a[NS];
         group_load_block<NS>(blk, li, a);
+        // logical row interchanges: each finished column is stored at its LINPACK position
+        // (every lane has its row in registers before the first group-wide reduction, so the
+        // in-place stores cannot overtake another lane's loads)
         int ipv;
-        int inf = group_dgefa<NS>(a, li, ipv);
+        const int inf = group_dgefa_track<NS, false>(a, li, ipv, [&](int col, int pos, double val) {
+            if (live && li < NS) blk[col * NS + pos] = val;
+        });
         if (live && li < NS) {
-#pragma unroll
-            for (int j = 0; j < NS; ++j) blk[j * NS + li] = a[j];
             ipbd[p * NS + li] = ipv;
             if (li == 0) {
                 if (info) info[p] = inf;
                 if (inf != 0 && first_flag) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
             }
         }
+    }
+}
+
+// dgesl on the reference layout, one THREAD per block: the substitution chains of 32 blocks are
+// interleaved in a warp and there are no shuffles.  A thread walks its own contiguous block, so a
+// warp-wide load touches 32 different lines; each 32-byte sector is consumed by 4 consecutive loads
+// of the same thread and stays in L1 in between, which keeps DRAM traffic at one pass over bd.
+template <int NS>
+__global__ void __launch_bounds__(128) dgesl_tpp_ref_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
+                                                            i64 nblk, double *__restrict__ bv)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < nblk; p += stride) {
+        const double *a = bd + p * (NS * NS);
+        const int *pv = ipbd + p * NS;
+        double b[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) b[i] = bv[p * NS + i];
+#pragma unroll
+        for (int k = 0; k < NS - 1; ++k) {
+            const int l = __ldg(pv + k) - 1;
+            double col[NS];
+#pragma unroll
+            for (int i = k + 1; i < NS; ++i) col[i] = __ldg(a + k * NS + i);
+            const double bk = b[k];
+            double t = bk;
+#pragma unroll
+            for (int i = k + 1; i < NS; ++i)
+                if (i == l) {
+                    t = b[i];
+                    b[i] = bk;
+                }
+            b[k] = t;
+#pragma unroll
+            for (int i = k + 1; i < NS; ++i) b[i] = b[i] + t * col[i];
+        }
+#pragma unroll
+        for (int k = NS - 1; k >= 0; --k) {
+            double col[NS];
+#pragma unroll
+            for (int i = 0; i <= k; ++i) col[i] = __ldg(a + k * NS + i);
+            b[k] = b[k] / col[k];
+            const double t = -b[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) b[i] = b[i] + t * col[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) bv[p * NS + i] = b[i];
     }
 }
 
@@ -172,7 +224,8 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
 {
     if (nblk <= 0) return 0;
     cudaStream_t st = g_ctx->stream;
-#define CALL(N) dgesl_kernel<N><<<lu_grid(nblk, GroupOf<N>::G), 256, 0, st>>>(bd, ipbd, nblk, b)
+    const int grid = (int)std::min<i64>((nblk + 127) / 128, 148 * 16);
+#define CALL(N) dgesl_tpp_ref_kernel<N><<<grid, 128, 0, st>>>(bd, ipbd, nblk, b)
     NS_DISPATCH(ns, CALL)
 #undef CALL
     COUNT_LAUNCH();
