@@ -31,13 +31,23 @@ __global__ void __launch_bounds__(256) dgefa_kernel(double *bd, int *ipbd, i64 n
         double *blk = bd + p * (NS * NS);
         double a[NS];
         group_load_block<NS>(blk, li, a);
-        // logical row interchanges: each finished column is stored at its LINPACK position
-        // (every lane has its row in registers before the first group-wide reduction, so the
-        // in-place stores cannot overtake another lane's loads)
-        int ipv;
-        const int inf = group_dgefa_track<NS, false>(a, li, ipv, [&](int col, int pos, double val) {
-            if (live && li < NS) blk[col * NS + pos] = val;
-        });
+        int ipv, inf;
+        if (NS >= 10) {
+            // logical row interchanges: each finished column is stored at its LINPACK position
+            // (every lane has its row in registers before the first group-wide reduction, so the
+            // in-place stores cannot overtake another lane's loads).  Faster than the exchanging
+            // variant from ns ~ 10 up (measured, tools/bench_extra.py); for small blocks the three
+            // warp reductions per step cost more than the butterfly they replace.
+            inf = group_dgefa_track<NS, false>(a, li, ipv, [&](int col, int pos, double val) {
+                if (live && li < NS) blk[col * NS + pos] = val;
+            });
+        } else {
+            inf = group_dgefa<NS>(a, li, ipv);
+            if (live && li < NS) {
+#pragma unroll
+                for (int j = 0; j < NS; ++j) blk[j * NS + li] = a[j];
+            }
+        }
         if (live && li < NS) {
             ipbd[p * NS + li] = ipv;
             if (li == 0) {
@@ -224,10 +234,18 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
 {
     if (nblk <= 0) return 0;
     cudaStream_t st = g_ctx->stream;
-    const int grid = (int)std::min<i64>((nblk + 127) / 128, 148 * 16);
+    // measured (tools/bench_extra.py, 1e6 blocks): one thread per block wins for ns <= 2 and ns >= 20,
+    // one sub-warp group per block in between
+    if (ns <= 2 || ns >= 20) {
+        const int grid = (int)std::min<i64>((nblk + 127) / 128, 148 * 16);
 #define CALL(N) dgesl_tpp_ref_kernel<N><<<grid, 128, 0, st>>>(bd, ipbd, nblk, b)
-    NS_DISPATCH(ns, CALL)
+        NS_DISPATCH(ns, CALL)
 #undef CALL
+    } else {
+#define CALL(N) dgesl_kernel<N><<<lu_grid(nblk, GroupOf<N>::G), 256, 0, st>>>(bd, ipbd, nblk, b)
+        NS_DISPATCH(ns, CALL)
+#undef CALL
+    }
     COUNT_LAUNCH();
     return 0;
 }
