@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The CUDA library is a build product (git-ignored): compile it for sm_100a if this checkout
+    has not been built yet (nvcc cross-compiles without a GPU; __graft_entry__.build() does the same)."""
+    from daskr_b200 import build as b
+
+    srcs = [os.path.join(b.CSRC, f) for f in os.listdir(b.CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(ROOT, "include", "daskr_b200.h"))
+    if not os.path.exists(b.LIB) or any(os.path.getmtime(s) > os.path.getmtime(b.LIB) for s in srcs):
+        b.build_cuda()
+    yield
+
+
 @pytest.fixture(scope="session")
 def oracle():
     """CPU oracle (oracle/), built on demand.  Test infrastructure only."""

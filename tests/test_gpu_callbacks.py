@@ -1,0 +1,169 @@
+"""User-callback path and error conventions, GPU vs oracle with the SAME injected faults.
+
+The callbacks are Python functions with the reference's argument lists (res_t / jack_t / psol_t,
+src/daskr_new.f90:11-71) that forward to the built-in problem routines -- device pointers on the GPU
+side, host pointers on the oracle side -- and inject return codes at chosen call numbers:
+  psol ier > 0  -> dspigm iflag=3 -> dslvk iersl=1 -> Newton failure -> refresh preconditioner, retry
+  psol ier < 0  -> iersl=-1 -> idid=-13
+  res ires = -1 -> recoverable: step retried with h/4;   ires = -2 -> idid=-11
+  jac ierr /= 0 -> idid=-5 (after the retries DASKR allows)
+Both sides must end with the same idid and, for the recoverable faults, the same counters and
+solutions within tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RES_T = C.CFUNCTYPE(None, *([C.c_void_p] * 8))
+JACK_T = C.CFUNCTYPE(None, *([C.c_void_p] * 16))
+PSOL_T = C.CFUNCTYPE(None, *([C.c_void_p] * 15))
+
+NP, MX, MY = 1, 20, 20
+NS = 2 * NP
+NEQ = NS * MX * MY
+TOUTS = [1e-8, 1e-6, 1e-4, 1e-3]
+
+
+class Faults:
+    def __init__(self, psol_at=None, psol_code=0, res_at=None, res_code=0, jac_at=None, jac_code=0):
+        self.psol_at, self.psol_code = psol_at, psol_code
+        self.res_at, self.res_code = res_at, res_code
+        self.jac_at, self.jac_code = jac_at, jac_code
+        self.n_res = self.n_psol = self.n_jac = 0
+
+
+def _int_at(addr):
+    return C.cast(addr, C.POINTER(C.c_int))
+
+
+def make_callbacks(L, prefix, f):
+    """prefix: 'dkb_web_' (GPU library) or 'o_web_' (oracle)."""
+    res_c = getattr(L, prefix + "res")
+    jac_c = getattr(L, prefix + "jac")
+    psol_c = getattr(L, prefix + "psol")
+    for fn, n in ((res_c, 8), (jac_c, 16), (psol_c, 15)):
+        fn.argtypes = [C.c_void_p] * n
+        fn.restype = None
+
+    def res(t, y, yd, cj, delta, ires, rpar, ipar):
+        f.n_res += 1
+        res_c(t, y, yd, cj, delta, ires, rpar, ipar)
+        if f.res_at is not None and f.n_res == f.res_at:
+            _int_at(ires)[0] = f.res_code
+
+    def jac(resf, ires, neq, t, y, yd, rewt, savr, wk, h, cj, rwp, iwp, ierr, rpar, ipar):
+        f.n_jac += 1
+        jac_c(resf, ires, neq, t, y, yd, rewt, savr, wk, h, cj, rwp, iwp, ierr, rpar, ipar)
+        if f.jac_at is not None and f.n_jac >= f.jac_at:
+            _int_at(ierr)[0] = f.jac_code
+
+    def psol(neq, t, y, yd, savr, wk, cj, wght, rwp, iwp, b, eps, ier, rpar, ipar):
+        f.n_psol += 1
+        psol_c(neq, t, y, yd, savr, wk, cj, wght, rwp, iwp, b, eps, ier, rpar, ipar)
+        if f.psol_at is not None and f.n_psol == f.psol_at:
+            _int_at(ier)[0] = f.psol_code
+
+    return RES_T(res), JACK_T(jac), PSOL_T(psol)
+
+
+def run_gpu(dk, faults):
+    iwork = np.zeros(40 + NEQ, dtype=np.int32)
+    dk.setup_rbdpre(MX, MY, NS, NP, 40, iwork)
+    dk.web_setpar(NP, MX, MY)
+    res, jac, psol = make_callbacks(dk.lib(), "dkb_web_", faults)
+    info = np.zeros(20, dtype=np.int32)
+    info[[10, 11, 13, 14, 15]] = 1
+    rwork, rpar, ipar = np.zeros(60), np.zeros(1), np.array([1, 0], dtype=np.int32)
+    c, cdot = dk.web_cinit(NEQ)
+    t, idid = dk.daskr(res, NEQ, 0.0, c, cdot, TOUTS[0], info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, jac, psol)
+    ys = []
+    if idid >= 0:
+        info[10] = 0
+        for tout in TOUTS:
+            t, idid = dk.daskr(res, NEQ, t, c, cdot, tout, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, jac, psol)
+            ys.append(c.copy())
+            if idid < 0:
+                break
+    return idid, np.array(ys), iwork[:40].copy(), faults
+
+
+def run_oracle(oracle, faults):
+    L = oracle.L
+    L.o_web_setpar(NP, MX, MY)
+    iwork = np.zeros(40 + 2 * NEQ + 16, dtype=np.int32)
+    L.o_setup_rbdpre(MX, MY, NS, NP, 40, iwork.ctypes.data_as(C.c_void_p))
+    lenwp = int(iwork[26])
+    lrw = 104 + 19 * NEQ + lenwp + 64
+    rwork = np.zeros(lrw)
+    res, jac, psol = make_callbacks(L, "o_web_", faults)
+    info = np.zeros(20, dtype=np.int32)
+    info[[10, 11, 13, 14, 15]] = 1
+    rpar, ipar = np.zeros(NEQ), np.array([1, 0], dtype=np.int32)
+    c, cdot = oracle.web_cinit(NP, MX, MY)
+    L.o_daskr.argtypes = [C.c_void_p] * 21
+    L.o_daskr.restype = None
+
+    def call(t, tout):
+        neq, nrt, idid, jroot = C.c_int(NEQ), C.c_int(0), C.c_int(0), C.c_int(0)
+        tc, toutc = C.c_double(t), C.c_double(tout)
+        rt, at = C.c_double(1e-5), C.c_double(1e-5)
+        lrwc, liwc = C.c_long(lrw), C.c_long(iwork.size)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        r = lambda x: C.cast(C.byref(x), C.c_void_p)  # noqa: E731
+        L.o_daskr(C.cast(res, C.c_void_p), r(neq), r(tc), p(c), p(cdot), r(toutc), p(info), r(rt), r(at), r(idid),
+                  p(rwork), r(lrwc), p(iwork), r(liwc), p(rpar), p(ipar), C.cast(jac, C.c_void_p),
+                  C.cast(psol, C.c_void_p), None, r(nrt), r(jroot))
+        return tc.value, idid.value
+
+    t, idid = call(0.0, TOUTS[0])
+    ys = []
+    if idid >= 0:
+        info[10] = 0
+        for tout in TOUTS:
+            t, idid = call(t, tout)
+            ys.append(c.copy())
+            if idid < 0:
+                break
+    return idid, np.array(ys), iwork[:40].copy(), faults
+
+
+def _compare(g, o, expect_idid):
+    assert g[0] == o[0] == expect_idid, (g[0], o[0])
+    assert (g[3].n_res, g[3].n_psol, g[3].n_jac) == (o[3].n_res, o[3].n_psol, o[3].n_jac)
+    assert np.array_equal(g[2][[10, 11, 12, 13, 14, 15, 18, 19, 20]], o[2][[10, 11, 12, 13, 14, 15, 18, 19, 20]])
+    if len(o[1]):
+        w = 1.0 / (1e-5 * np.abs(o[1]) + 1e-5)
+        assert np.sqrt(np.mean(((g[1] - o[1]) * w) ** 2, axis=1)).max() <= 10.0
+
+
+def test_callbacks_no_fault(dk, oracle):
+    _compare(run_gpu(dk, Faults()), run_oracle(oracle, Faults()), 3)
+
+
+@pytest.mark.parametrize("at", [9, 31])
+def test_psol_recoverable(dk, oracle, at):
+    g = run_gpu(dk, Faults(psol_at=at, psol_code=1))
+    o = run_oracle(oracle, Faults(psol_at=at, psol_code=1))
+    _compare(g, o, 3)
+    assert g[2][15] >= 1   # NCFL: one linear convergence failure recorded
+
+
+def test_psol_fatal(dk, oracle):
+    g = run_gpu(dk, Faults(psol_at=25, psol_code=-1))
+    o = run_oracle(oracle, Faults(psol_at=25, psol_code=-1))
+    _compare(g, o, -13)
+
+
+def test_res_recoverable_and_fatal(dk, oracle):
+    _compare(run_gpu(dk, Faults(res_at=30, res_code=-1)), run_oracle(oracle, Faults(res_at=30, res_code=-1)), 3)
+    _compare(run_gpu(dk, Faults(res_at=30, res_code=-2)), run_oracle(oracle, Faults(res_at=30, res_code=-2)), -11)
+
+
+def test_jac_failure(dk, oracle):
+    g = run_gpu(dk, Faults(jac_at=6, jac_code=3))
+    o = run_oracle(oracle, Faults(jac_at=6, jac_code=3))
+    assert g[0] == o[0] and g[0] < 0, (g[0], o[0])
+    assert np.array_equal(g[2][[10, 12, 14]], o[2][[10, 12, 14]])
