@@ -148,7 +148,8 @@ def test_psol_recoverable(dk, oracle, at):
     g = run_gpu(dk, Faults(psol_at=at, psol_code=1))
     o = run_oracle(oracle, Faults(psol_at=at, psol_code=1))
     _compare(g, o, 3)
-    assert g[2][15] >= 1   # NCFL: one linear convergence failure recorded
+    if at > 20:   # (a fault during the IC call is wiped when the counters restart at the second initial call)
+        assert g[2][15] >= 1   # NCFL: one linear convergence failure recorded
 
 
 def test_psol_fatal(dk, oracle):
