@@ -8,7 +8,7 @@
  *   ddasik / dnsik / dlinsk / dfnrmk (:2004-2658),
  *   dnedk / dnsk (:2660-3034).
  * Not restated (out of the hot-path scope): the
- * direct dense/banded solvers, rootfinding (nrt must be 0) and the XERRWD
+ * direct dense/banded solvers and the XERRWD
  * message printer (idid codes are returned, messages are not printed).
  * The work arrays keep the reference's layout so that
  * rwork(1:60) / iwork(1:40) can be compared slot for slot.
@@ -798,6 +798,237 @@ static void ddstp(double *t, double *y, double *ydot, long neq, o_res_t res, o_j
 }
 #undef PHI
 
+/* callback contract of the root functions, src/daskr.f:908-934 (RT) */
+typedef void (*o_rt_t)(const int *neq, const double *t, const double *y, const double *yp, const int *nrt,
+                       double *rval, double *rpar, int *ipar);
+
+static inline double sign1(double x) { return std::signbit(x) ? -1.0 : 1.0; } /* SIGN(1.0D0,x) */
+
+/* DROOTS, src/daskr.f:2676-2910.  SAVEd: alpha, x2, imax, last. */
+static void droots(int nrt, double hmin, int *jflag, double *x0, double *x1, double *r0, double *r1,
+                   double *rx, double *x, int *jroot)
+{
+    static double alpha, x2;
+    static int imax, last;
+    int imxold, nxlast = 0;
+    double t2, tmax, fracint, fracsub;
+    bool zroot, sgnchg, xroot = false;
+
+    if (*jflag == 1) goto L200;
+    /* first call: look for sign changes in (x0, x1) */
+    imax = 0;
+    tmax = 0.0;
+    zroot = false;
+    for (int i = 0; i < nrt; ++i) {
+        if (!(std::fabs(r1[i]) > 0.0)) { zroot = true; continue; }
+        if (sign1(r0[i]) == sign1(r1[i])) continue;
+        t2 = std::fabs(r1[i] / (r1[i] - r0[i]));
+        if (t2 <= tmax) continue;
+        tmax = t2;
+        imax = i + 1;
+    }
+    sgnchg = imax > 0;
+    if (!sgnchg) goto L400;
+    xroot = false;
+    nxlast = 0;
+    last = 1;
+
+L150:
+    if (xroot) goto L300;
+    if (nxlast != last)
+        alpha = 1.0;
+    else if (last != 0)
+        alpha = 0.5 * alpha;
+    else
+        alpha = 2.0 * alpha;
+    x2 = *x1 - (*x1 - *x0) * r1[imax - 1] / (r1[imax - 1] - alpha * r0[imax - 1]);
+    if (std::fabs(x2 - *x0) < 0.5 * hmin) {
+        fracint = std::fabs(*x1 - *x0) / hmin;
+        fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+        x2 = *x0 + fracsub * (*x1 - *x0);
+    }
+    if (std::fabs(*x1 - x2) < 0.5 * hmin) {
+        fracint = std::fabs(*x1 - *x0) / hmin;
+        fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+        x2 = *x1 - fracsub * (*x1 - *x0);
+    }
+    *jflag = 1;
+    *x = x2;
+    return;
+
+L200:
+    /* re-entry with rx = r(x2): narrow the bracket */
+    imxold = imax;
+    imax = 0;
+    tmax = 0.0;
+    zroot = false;
+    for (int i = 0; i < nrt; ++i) {
+        if (!(std::fabs(rx[i]) > 0.0)) { zroot = true; continue; }
+        if (sign1(r0[i]) == sign1(rx[i])) continue;
+        t2 = std::fabs(rx[i] / (rx[i] - r0[i]));
+        if (t2 <= tmax) continue;
+        tmax = t2;
+        imax = i + 1;
+    }
+    if (imax > 0) {
+        sgnchg = true;
+    } else {
+        sgnchg = false;
+        imax = imxold;
+    }
+    nxlast = last;
+    if (sgnchg) {
+        *x1 = x2;
+        for (int i = 0; i < nrt; ++i) r1[i] = rx[i];
+        last = 1;
+        xroot = false;
+    } else if (zroot) {
+        *x1 = x2;
+        for (int i = 0; i < nrt; ++i) r1[i] = rx[i];
+        xroot = true;
+    } else {
+        for (int i = 0; i < nrt; ++i) r0[i] = rx[i];
+        *x0 = x2;
+        last = 0;
+        xroot = false;
+    }
+    if (std::fabs(*x1 - *x0) <= hmin) xroot = true;
+    goto L150;
+
+L300:
+    *jflag = 2;
+    *x = *x1;
+    for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+    for (int i = 0; i < nrt; ++i) {
+        jroot[i] = 0;
+        if (std::fabs(r1[i]) == 0.0) {
+            jroot[i] = (int)(-sign1(r0[i]));
+            continue;
+        }
+        if (sign1(r0[i]) != sign1(r1[i])) jroot[i] = (int)sign1(r1[i] - r0[i]);
+    }
+    return;
+
+L400:
+    if (zroot) {
+        *x = *x1;
+        for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+        for (int i = 0; i < nrt; ++i) {
+            jroot[i] = 0;
+            if (std::fabs(r1[i]) == 0.0) jroot[i] = (int)(-sign1(r0[i]));
+        }
+        *jflag = 3;
+        return;
+    }
+    for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+    *x = *x1;
+    *jflag = 4;
+}
+
+/* DRCHEK, src/daskr.f:2494-2675 */
+static void drchek(int job, o_rt_t rt, int nrt, long neq, double tn, double tout, double *y, double *yp,
+                   double *phi, double *psi, int kold, double *r0, double *r1, double *rx, int *jroot,
+                   int *irt, double uround, int info3, double *rwork, int *iwork, double *rpar, int *ipar)
+{
+    (void)info3;
+    double *RW = rwork - 1;
+    int *IW = iwork - 1;
+    const int neq32 = (int)neq;
+    const double h = psi[0];
+    double t1, temp1, temp2, x = 0.0;
+    bool zroot;
+    int jflag;
+    *irt = 0;
+    for (int i = 0; i < nrt; ++i) jroot[i] = 0;
+    const double hminr = (std::fabs(tn) + std::fabs(h)) * uround * 100.0;
+
+    if (job == 1) {
+        /* evaluate R at the initial T (= RWORK(LT0)); check for zero values */
+        o_ddatrp(tn, RW[LT0], y, yp, neq, kold, phi, psi);
+        rt(&neq32, &RW[LT0], y, yp, &nrt, r0, rpar, ipar);
+        IW[LNRTE] = 1;
+        zroot = false;
+        for (int i = 0; i < nrt; ++i)
+            if (std::fabs(r0[i]) == 0.0) zroot = true;
+        if (!zroot) return;
+        /* R has a zero at T: look at R at T + (small increment) */
+        temp2 = std::max(hminr / std::fabs(h), 0.1);
+        temp1 = temp2 * h;
+        RW[LT0] = RW[LT0] + temp1;
+        for (long i = 0; i < neq; ++i) y[i] = y[i] + temp2 * phi[neq + i];
+        rt(&neq32, &RW[LT0], y, yp, &nrt, r0, rpar, ipar);
+        IW[LNRTE] = IW[LNRTE] + 1;
+        zroot = false;
+        for (int i = 0; i < nrt; ++i)
+            if (std::fabs(r0[i]) == 0.0) zroot = true;
+        if (zroot) *irt = -1;
+        return;
+    }
+    if (job == 2) {
+        if (IW[LIRFND] != 0) {
+            /* a root was found on the previous step: evaluate R0 = R(T0) */
+            o_ddatrp(tn, RW[LT0], y, yp, neq, kold, phi, psi);
+            rt(&neq32, &RW[LT0], y, yp, &nrt, r0, rpar, ipar);
+            IW[LNRTE] = IW[LNRTE] + 1;
+            zroot = false;
+            for (int i = 0; i < nrt; ++i)
+                if (std::fabs(r0[i]) == 0.0) {
+                    zroot = true;
+                    jroot[i] = 1;
+                }
+            if (zroot) {
+                /* R has a zero at T0: look at R at T0 + (small increment) */
+                temp1 = (h >= 0.0) ? std::fabs(hminr) : -std::fabs(hminr);
+                RW[LT0] = RW[LT0] + temp1;
+                if ((RW[LT0] - tn) * h < 0.0) {
+                    o_ddatrp(tn, RW[LT0], y, yp, neq, kold, phi, psi);
+                } else {
+                    temp2 = temp1 / h;
+                    for (long i = 0; i < neq; ++i) y[i] = y[i] + temp2 * phi[neq + i];
+                }
+                rt(&neq32, &RW[LT0], y, yp, &nrt, r0, rpar, ipar);
+                IW[LNRTE] = IW[LNRTE] + 1;
+                for (int i = 0; i < nrt; ++i) {
+                    if (std::fabs(r0[i]) > 0.0) continue;
+                    if (jroot[i] == 1) {   /* R_i has a zero at T0 and also close to T0 */
+                        *irt = -2;
+                        return;
+                    }
+                    jroot[i] = (int)(-sign1(r0[i]));
+                    *irt = 1;
+                }
+                if (*irt == 1) return;
+            }
+        }
+        /* R0 has no zero components: proceed to check the relevant interval */
+        if (tn == RW[LTLAST]) return;
+    }
+    /* job == 3 (and the tail of job == 2): set T1 to TN or TOUT, whichever comes first, and get R there */
+    if ((tout - tn) * h >= 0.0) {
+        t1 = tn;
+    } else {
+        t1 = tout;
+        if ((t1 - RW[LT0]) * h <= 0.0) return;
+    }
+    o_ddatrp(tn, t1, y, yp, neq, kold, phi, psi);
+    rt(&neq32, &t1, y, yp, &nrt, r1, rpar, ipar);
+    IW[LNRTE] = IW[LNRTE] + 1;
+    jflag = 0;
+    for (;;) {
+        droots(nrt, hminr, &jflag, &RW[LT0], &t1, r0, r1, rx, &x, jroot);
+        if (jflag > 1) break;
+        o_ddatrp(tn, x, y, yp, neq, kold, phi, psi);
+        rt(&neq32, &x, y, yp, &nrt, rx, rpar, ipar);
+        IW[LNRTE] = IW[LNRTE] + 1;
+    }
+    RW[LT0] = x;
+    for (int i = 0; i < nrt; ++i) r0[i] = rx[i];
+    if (jflag == 4) return;
+    /* found a root: interpolate to X and return */
+    o_ddatrp(tn, x, y, yp, neq, kold, phi, psi);
+    *irt = 1;
+}
+
 extern "C" {
 
 /* SAVEd between calls, src/daskr.f:1429 */
@@ -806,14 +1037,15 @@ static int s_lenid, s_nonneg, s_ncphi;
 
 /* src/daskr.f:1-2493, Krylov option.  lrw/liw are 64-bit here so that CPU
  * baselines at 1024^2 x 20 (LENRW ~ 8e8) stay addressable; every other
- * argument is as in the reference.  rt/nrt/jroot: nrt must be 0. */
+ * argument is as in the reference (rt is an o_rt_t passed as void*). */
 void o_daskr(o_res_t res, const int *neq_, double *t, double *y, double *yprime,
              const double *tout_, int *info, double *rtol, double *atol,
              int *idid, double *rwork, const long *lrw, int *iwork,
              const long *liw, double *rpar, int *ipar, o_jack_t jac,
              o_psol_t psol, void *rt, const int *nrt_, int *jroot)
 {
-    (void)rt; (void)jroot;
+    o_rt_t rtf = (o_rt_t)rt;
+    int irt = 0;
     const long neq = *neq_;
     const int nrt = *nrt_;
     const double tout = *tout_;
@@ -847,7 +1079,7 @@ void o_daskr(o_res_t res, const int *neq_, double *t, double *y, double *yprime,
     if (INFO[18] < 0 || INFO[18] > 2) goto L701;
     if (neq <= 0) goto L701;
     if (INFO[12] != 1) goto L701; /* oracle restates the Krylov option only */
-    if (nrt != 0) goto L701;      /* rootfinding not restated */
+    if (nrt < 0) goto L701;
 
     mxord = 5;
     if (INFO[9] != 0) {
@@ -1121,6 +1353,11 @@ L200:
     RW[LPSI] = h;
     RW[LPSI + 1] = 2.0 * h;
     IW[LKOLD] = 1;
+    if (nrt != 0) {   /* check for a zero of R near the initial T (:1929-1934) */
+        drchek(1, rtf, nrt, neq, *t, tout, y, yprime, &RW[lphi], &RW[LPSI], IW[LKOLD], &RW[lr0], &RW[lr1],
+               &RW[lrx], jroot, &irt, RW[LROUND], INFO[3], rwork, iwork, rpar, ipar);
+        if (irt < 0) goto L701;
+    }
     goto L500;
 
     /* ---- continuation: stop tests before stepping (:1944-2042) ---- */
@@ -1129,6 +1366,18 @@ L400:
     done = false;
     tn = RW[LTN];
     h = RW[LH];
+    if (nrt != 0) {   /* check for a zero of R near TN (:1949-1963) */
+        drchek(2, rtf, nrt, neq, tn, tout, y, yprime, &RW[lphi], &RW[LPSI], IW[LKOLD], &RW[lr0], &RW[lr1],
+               &RW[lrx], jroot, &irt, RW[LROUND], INFO[3], rwork, iwork, rpar, ipar);
+        if (irt < 0) goto L701;
+        if (irt == 1) {
+            IW[LIRFND] = 1;
+            *idid = 5;
+            *t = RW[LT0];
+            done = true;
+            goto L490;
+        }
+    }
     if (INFO[7] != 0) {
         rh = std::fabs(h) / RW[LHMAX];
         if (rh > 1.0) h = h / rh;
@@ -1244,7 +1493,17 @@ L500:
 L527:
     if (*idid < 0) goto L600;
 
-    /* ---- successful step: stop tests (:2191-2245) ---- */
+    /* ---- successful step: root check (:2177-2189), then stop tests (:2191-2245) ---- */
+    if (nrt != 0) {
+        drchek(3, rtf, nrt, neq, tn, tout, y, yprime, &RW[lphi], &RW[LPSI], IW[LKOLD], &RW[lr0], &RW[lr1],
+               &RW[lrx], jroot, &irt, RW[LROUND], INFO[3], rwork, iwork, rpar, ipar);
+        if (irt == 1) {
+            IW[LIRFND] = 1;
+            *idid = 5;
+            *t = RW[LT0];
+            goto L590;
+        }
+    }
     if (INFO[4] == 0) {
         if ((tn - tout) * h >= 0.0) {
             o_ddatrp(tn, tout, y, yprime, neq, IW[LKOLD], &RW[lphi], &RW[LPSI]);

@@ -125,12 +125,16 @@ void o_web_psol(const int *neq, const double *t, const double *c,
                 double *b, const double *epslin, int *ierr, double *rpar, int *ipar);
 void o_web_gauss_seidel(long n, double hl0, double *z, double *x);
 double o_web_c1_average(const double *c);
+void o_web_rt(const int *neq, const double *t, const double *c, const double *cdot, const int *nrt,
+              double *rval, double *rpar, int *ipar);   /* example_web.f90:600-617 */
 
 /* ---- heat problem, example/example_heat.f90 (+ rbdpre ns=1 pairing) ---- */
 void o_heat_setpar(int m);
 void o_heat_uinit(double *u, double *udot);
 void o_heat_res(const double *t, const double *u, const double *udot,
                 const double *cj, double *delta, int *ires, double *rpar, int *ipar);
+void o_heat_rt(const int *neq, const double *t, const double *u, const double *udot, const int *nrt,
+               double *rval, double *rpar, int *ipar);  /* example_heat.f90:91-109 */
 void o_heat_jac(o_res_t res, int *ires, const int *neq, const double *t, double *u,
                 double *udot, const double *rewt, double *savr, double *wk,
                 const double *h, const double *cj, double *rwp, int *iwp,

@@ -383,6 +383,14 @@ double o_web_c1_average(const double *c)
     return total / ((double)w_mx * w_my);
 }
 
+/* example/example_web.f90:600-617: root function average(c1) - 20 */
+void o_web_rt(const int *neq, const double *t, const double *c, const double *cdot, const int *nrt,
+              double *rval, double *rpar, int *ipar)
+{
+    (void)neq; (void)t; (void)cdot; (void)nrt; (void)rpar; (void)ipar;
+    rval[0] = o_web_c1_average(c) - 20.0;
+}
+
 /* ------------------------------------------------------------------ */
 /* heat: example/example_heat.f90                                      */
 /* ------------------------------------------------------------------ */
@@ -433,6 +441,17 @@ void o_heat_res(const double *t, const double *u, const double *udot, const doub
             delta[i] = udot[i] - (temx + temy - 4 * u[i]) * coeff;
         }
     }
+}
+
+/* example/example_heat.f90:91-109: roots at max(u) = 0.1 and 0.01 */
+void o_heat_rt(const int *neq, const double *t, const double *u, const double *udot, const int *nrt,
+               double *rval, double *rpar, int *ipar)
+{
+    (void)t; (void)udot; (void)nrt; (void)rpar; (void)ipar;
+    double umax = u[0];
+    for (long i = 1; i < *neq; ++i) umax = std::max(umax, u[i]);
+    rval[0] = umax - 0.1;
+    rval[1] = umax - 0.01;
 }
 
 /* rbdpre pairing for the heat problem (ns = nsd = 1).  NOT shipped by the
