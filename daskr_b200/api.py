@@ -31,7 +31,7 @@ EXPORTS = [
     "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
     "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
-    "dkb_heat_psol", "dkb_heat_uinit", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
+    "dkb_heat_psol", "dkb_heat_uinit", "dkb_web_rt", "dkb_heat_rt", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
     "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
@@ -108,6 +108,7 @@ class _LazyFn:
 
 WEB_RES, WEB_JAC, WEB_PSOL = _LazyFn("dkb_web_res"), _LazyFn("dkb_web_jac"), _LazyFn("dkb_web_psol")
 HEAT_RES, HEAT_JAC, HEAT_PSOL = _LazyFn("dkb_heat_res"), _LazyFn("dkb_heat_jac"), _LazyFn("dkb_heat_psol")
+WEB_RT, HEAT_RT = _LazyFn("dkb_web_rt"), _LazyFn("dkb_heat_rt")
 
 
 def init(device=0):
@@ -190,25 +191,29 @@ def _ptr_of(a):
     return _p(a)
 
 
-def daskr(res, neq, t, y, ydot, tout, info, rtol, atol, rwork, iwork, rpar, ipar, jac, psol, nrt=0):
+def daskr(res, neq, t, y, ydot, tout, info, rtol, atol, rwork, iwork, rpar, ipar, jac, psol, rt=None, nrt=0,
+          jroot=None):
     """DASKR(RES,NEQ,T,Y,YPRIME,TOUT,INFO,RTOL,ATOL,IDID,RWORK,LRW,IWORK,LIW,RPAR,IPAR,JAC,PSOL,RT,NRT,JROOT)
     -- src/daskr.f:1-3, Krylov option.  y/ydot: float64 numpy arrays (host) or device addresses
     (with OPT_DEVICE_IO); info/iwork/ipar int32, rwork/rpar float64, modified in place.
-    Returns (t, idid)."""
+    rt: root routine (dkb_rt_t: device y/yprime in, nrt host values out) with nrt > 0; jroot: int32[nrt],
+    filled when idid == 5.  rwork needs 60 + 3*nrt words.  Returns (t, idid)."""
     assert info.dtype == np.int32 and iwork.dtype == np.int32 and rwork.dtype == np.float64
     neq_c, nrt_c, idid_c = C.c_int(int(neq)), C.c_int(int(nrt)), C.c_int(0)
     t_c, tout_c = C.c_double(float(t)), C.c_double(float(tout))
     rtol_a = np.atleast_1d(np.asarray(rtol, dtype=np.float64))
     atol_a = np.atleast_1d(np.asarray(atol, dtype=np.float64))
     lrw, liw = C.c_int64(rwork.size), C.c_int64(iwork.size)
-    jroot = C.c_int(0)
+    if jroot is None:
+        jroot = np.zeros(max(int(nrt), 1), dtype=np.int32)
+    assert jroot.dtype == np.int32 and jroot.size >= nrt
     rp = _p(rpar) if rpar is not None else C.c_void_p(0)
     ip = _p(ipar) if ipar is not None else C.c_void_p(0)
     lib().dkb_daskr(
         _cbptr(res), _ref(neq_c), _ref(t_c), _ptr_of(y), _ptr_of(ydot),
         _ref(tout_c), _p(info), _p(rtol_a), _p(atol_a), _ref(idid_c),
         _p(rwork), _ref(lrw), _p(iwork), _ref(liw), rp, ip, _cbptr(jac),
-        _cbptr(psol), C.c_void_p(0), _ref(nrt_c), _ref(jroot),
+        _cbptr(psol), _cbptr(rt) if rt is not None else C.c_void_p(0), _ref(nrt_c), _p(jroot),
     )
     if idid_c.value == -33:
         raise DaskrError("daskr: illegal input (idid=-33): %s" % lib().dkb_last_error().decode())
@@ -308,11 +313,13 @@ def launch_count():
 
 # ---------------------------------------------------------------- whole-run drivers
 def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fused=True, ic=True, pred_ic=None,
-              y_out=True):
+              y_out=True, roots=False):
     """The food-web example as example/example_web.f90:884-954 runs it (Krylov, no grouping, nrt=0):
     one DASKR call for consistent initial values (info(11)=1, info(14)=1 -> idid=4), then integration
     with outputs at `touts`.  Returns dict(y=[nout, neq], counters=[nout, 40], rhead=[nout, 60], idid, t).
-    With max_steps > 0 the run stops after that many BDF steps (info(3)=1 stepping)."""
+    With max_steps > 0 the run stops after that many BDF steps (info(3)=1 stepping).  roots=True adds the
+    example's root function (nrt=1, average(c1) - 20, example_web.f90:600-617); every idid=5 return is
+    recorded in result["roots"] as (t, jroot, counters) and the integration continues."""
     ns = 2 * np_
     iwork = np.zeros(40 + 1, dtype=np.int32)  # sized below once the slab is known
     probe = np.zeros(64, dtype=np.int32)
@@ -327,7 +334,11 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     info[11] = 1  # info(12): Krylov
     info[14] = 1  # info(15): jac supplied
     info[15] = 1  # info(16): error test on differential variables only
-    rwork = np.zeros(60)
+    nrt = 1 if roots else 0
+    rtf = WEB_RT if roots else None
+    jroot = np.zeros(1, dtype=np.int32)
+    found = []
+    rwork = np.zeros(60 + 3 * nrt)
     rpar = np.zeros(1)
     ipar = np.array([jpre, 0], dtype=np.int32)
     if pred_ic is None:
@@ -338,7 +349,8 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     if ic:
         info[10] = 1  # info(11)
         info[13] = 1  # info(14)
-        t, idid = daskr(WEB_RES, neq, t, c, cdot, touts[0], info, rtol, atol, rwork, iwork, rpar, ipar, WEB_JAC, WEB_PSOL)
+        t, idid = daskr(WEB_RES, neq, t, c, cdot, touts[0], info, rtol, atol, rwork, iwork, rpar, ipar, WEB_JAC, WEB_PSOL,
+                        rtf, nrt, jroot)
         if idid < 0:
             return dict(y=None, counters=iwork[:40].copy()[None], rhead=rwork[:60].copy()[None], idid=idid, t=t,
                         c0=c, cdot0=cdot)
@@ -350,9 +362,13 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     steps = 0
     for tout in touts:
         while True:
-            t, idid = daskr(WEB_RES, neq, t, c, cdot, tout, info, rtol, atol, rwork, iwork, rpar, ipar, WEB_JAC, WEB_PSOL)
+            t, idid = daskr(WEB_RES, neq, t, c, cdot, tout, info, rtol, atol, rwork, iwork, rpar, ipar, WEB_JAC, WEB_PSOL,
+                            rtf, nrt, jroot)
             if idid < 0:
                 break
+            if idid == 5:
+                found.append((t, jroot.copy(), iwork[:40].copy()))
+                continue
             if max_steps > 0 and idid == 1:
                 steps += 1
                 if steps >= max_steps:
@@ -366,11 +382,12 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
         if idid < 0 or (max_steps > 0 and steps >= max_steps):
             break
     return dict(y=np.array(ys) if y_out else None, counters=np.array(cnts), rhead=np.array(rhs), idid=idid, t=t,
-                c0=c0, cdot0=cdot0)
+                c0=c0, cdot0=cdot0, roots=found)
 
 
-def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=True):
-    """example/example_heat.f90:174-240 with the rbdpre ns=1 diagonal preconditioner (nrt=0)."""
+def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=True, roots=False):
+    """example/example_heat.f90:174-240 with the rbdpre ns=1 diagonal preconditioner.  roots=True adds the
+    example's two root functions (max(u) - 0.1, max(u) - 0.01, example_heat.f90:91-109)."""
     probe = np.zeros(64, dtype=np.int32)
     setup_rbdpre(m + 2, m + 2, 1, 1, 0, probe)
     _, myloc = slab()
@@ -382,7 +399,11 @@ def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=Tru
     info = np.zeros(20, dtype=np.int32)
     info[11] = 1
     info[14] = 1
-    rwork = np.zeros(60)
+    nrt = 2 if roots else 0
+    rtf = HEAT_RT if roots else None
+    jroot = np.zeros(2, dtype=np.int32)
+    found = []
+    rwork = np.zeros(60 + 3 * nrt)
     rpar = np.zeros(2)
     ipar = np.array([0, 0, neq, m], dtype=np.int32)
     u, ud = heat_uinit(neq)
@@ -394,9 +415,13 @@ def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=Tru
     steps = 0
     for tout in touts:
         while True:
-            t, idid = daskr(HEAT_RES, neq, t, u, ud, tout, info, rtol, atol, rwork, iwork, rpar, ipar, HEAT_JAC, HEAT_PSOL)
+            t, idid = daskr(HEAT_RES, neq, t, u, ud, tout, info, rtol, atol, rwork, iwork, rpar, ipar, HEAT_JAC, HEAT_PSOL,
+                            rtf, nrt, jroot)
             if idid < 0:
                 break
+            if idid == 5:
+                found.append((t, jroot.copy(), iwork[:40].copy()))
+                continue
             if max_steps > 0 and idid == 1:
                 steps += 1
                 if steps >= max_steps:
@@ -409,4 +434,5 @@ def solve_heat(m, touts, rtol=0.0, atol=1e-5, max_steps=0, fused=True, y_out=Tru
         rhs.append(rwork[:60].copy())
         if idid < 0 or (max_steps > 0 and steps >= max_steps):
             break
-    return dict(y=np.array(ys) if y_out else None, counters=np.array(cnts), rhead=np.array(rhs), idid=idid, t=t)
+    return dict(y=np.array(ys) if y_out else None, counters=np.array(cnts), rhead=np.array(rhs), idid=idid, t=t,
+                roots=found)

@@ -389,6 +389,22 @@ int dkb_web_setpar_ex(int np, int mx, int my, double ay)
     return 0;
 }
 
+static void require_problem(int prob, const char *who);
+
+// rt, example/example_web.f90:600-617: rval(1) = average of species 1 over the (global) mesh - 20.
+// Deterministic device sum of c(1,:,:) on this rank's rows, allreduce over ranks, one scalar back.
+void dkb_web_rt(const int *neq, const double *t, const double *cc, const double *cdot, const int *nrt, double *rval,
+                double *rpar, int *ipar)
+{
+    (void)neq; (void)t; (void)cdot; (void)nrt; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_WEB, "dkb_web_rt");
+    DkbCtx *c = g_ctx;
+    double total;
+    r_sum_strided((i64)c->mx * c->my, c->web.ns, 0, cc, 44);
+    scal_fetch(44, 1, &total);
+    rval[0] = total / (double)((i64)c->web.mx * c->web.my) - 20.0;
+}
+
 // cinit, example/example_web.f90:102-148, for this rank's rows (host arrays).  The prey rates
 // cdot = f(c) need the mesh neighbours, so the full rows jy0-1 .. jy0+my are generated locally
 // (the initial profile is a closed-form function of x and y).
@@ -586,6 +602,19 @@ int dkb_heat_uinit(double *u, double *udot)
         }
     }
     return 0;
+}
+
+// rt, example/example_heat.f90:91-109: rval = max(u) - 0.1, max(u) - 0.01
+void dkb_heat_rt(const int *neq, const double *t, const double *u, const double *udot, const int *nrt, double *rval,
+                 double *rpar, int *ipar)
+{
+    (void)t; (void)udot; (void)rpar; (void)ipar;
+    require_problem(DKB_PROB_HEAT, "dkb_heat_rt");
+    double umax;
+    r_max(*neq, u, 44);
+    scal_fetch(44, 1, &umax);
+    rval[0] = umax - 0.1;
+    if (*nrt > 1) rval[1] = umax - 0.01;
 }
 
 void dkb_heat_res(const double *t, const double *u, const double *udot, const double *cj, double *delta, int *ires,

@@ -28,7 +28,8 @@ enum { LML = 1, LMU = 2, LMTYPE = 4, LIWM = 1, LMXORD = 3, LJCALC = 5, LPHASE = 
 // rwork pointers, src/daskr.f:1424-1427
 enum { LTSTOP = 1, LHMAX = 2, LH = 3, LTN = 4, LCJ = 5, LCJOLD = 6, LHOLD = 7, LS = 8, LROUND = 9, LEPLI = 10,
        LSQRN = 11, LRSQRN = 12, LEPCON = 13, LSTOL = 14, LEPIN = 15, LALPHA = 21, LBETA = 27, LGAMMA = 33,
-       LPSI = 39, LSIGMA = 45, LT0 = 51, LTLAST = 52, LDELTA = 61 };
+       LPSI = 39, LSIGMA = 45, LT0 = 51, LTLAST = 52, LDELTA = 61,
+       LR0 = 61 };   // R0, R1, RX (3*nrt words) follow the scalar header: the vector segments live on the device
 
 static inline double dsign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
 
@@ -791,13 +792,228 @@ static void k_ddasic(DkbCtx *c, const Cb &cb, double x, int icopt, double *h, do
     *idid = -12;
 }
 
+// ---------------------------------------------------------------- rootfinding (DRCHEK / DROOTS)
+static inline double sign1(double x) { return signbit(x) ? -1.0 : 1.0; }   // SIGN(1.0D0, x)
+
+// DROOTS, src/daskr.f:2676-2910: scalar logic on the nrt root-function values (host).
+// SAVEd between calls: alpha, x2, imax, last.
+static void h_droots(int nrt, double hmin, int *jflag, double *x0, double *x1, double *r0, double *r1, double *rx,
+                     double *x, int *jroot)
+{
+    static double alpha, x2;
+    static int imax, last;
+    int imxold, nxlast = 0;
+    double t2, tmax, fracint, fracsub;
+    bool zroot, sgnchg, xroot = false;
+
+    if (*jflag == 1) goto L200;
+    imax = 0;
+    tmax = 0.0;
+    zroot = false;
+    for (int i = 0; i < nrt; ++i) {
+        if (!(fabs(r1[i]) > 0.0)) { zroot = true; continue; }
+        if (sign1(r0[i]) == sign1(r1[i])) continue;
+        t2 = fabs(r1[i] / (r1[i] - r0[i]));
+        if (t2 <= tmax) continue;
+        tmax = t2;
+        imax = i + 1;
+    }
+    sgnchg = imax > 0;
+    if (!sgnchg) goto L400;
+    xroot = false;
+    nxlast = 0;
+    last = 1;
+L150:
+    if (xroot) goto L300;
+    if (nxlast != last) alpha = 1.0;
+    else if (last != 0) alpha = 0.5 * alpha;
+    else alpha = 2.0 * alpha;
+    x2 = *x1 - (*x1 - *x0) * r1[imax - 1] / (r1[imax - 1] - alpha * r0[imax - 1]);
+    if (fabs(x2 - *x0) < 0.5 * hmin) {
+        fracint = fabs(*x1 - *x0) / hmin;
+        fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+        x2 = *x0 + fracsub * (*x1 - *x0);
+    }
+    if (fabs(*x1 - x2) < 0.5 * hmin) {
+        fracint = fabs(*x1 - *x0) / hmin;
+        fracsub = (fracint > 5.0) ? 0.1 : 0.5 / fracint;
+        x2 = *x1 - fracsub * (*x1 - *x0);
+    }
+    *jflag = 1;
+    *x = x2;
+    return;
+L200:
+    imxold = imax;
+    imax = 0;
+    tmax = 0.0;
+    zroot = false;
+    for (int i = 0; i < nrt; ++i) {
+        if (!(fabs(rx[i]) > 0.0)) { zroot = true; continue; }
+        if (sign1(r0[i]) == sign1(rx[i])) continue;
+        t2 = fabs(rx[i] / (rx[i] - r0[i]));
+        if (t2 <= tmax) continue;
+        tmax = t2;
+        imax = i + 1;
+    }
+    if (imax > 0) {
+        sgnchg = true;
+    } else {
+        sgnchg = false;
+        imax = imxold;
+    }
+    nxlast = last;
+    if (sgnchg) {
+        *x1 = x2;
+        for (int i = 0; i < nrt; ++i) r1[i] = rx[i];
+        last = 1;
+        xroot = false;
+    } else if (zroot) {
+        *x1 = x2;
+        for (int i = 0; i < nrt; ++i) r1[i] = rx[i];
+        xroot = true;
+    } else {
+        for (int i = 0; i < nrt; ++i) r0[i] = rx[i];
+        *x0 = x2;
+        last = 0;
+        xroot = false;
+    }
+    if (fabs(*x1 - *x0) <= hmin) xroot = true;
+    goto L150;
+L300:
+    *jflag = 2;
+    *x = *x1;
+    for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+    for (int i = 0; i < nrt; ++i) {
+        jroot[i] = 0;
+        if (fabs(r1[i]) == 0.0) {
+            jroot[i] = (int)(-sign1(r0[i]));
+            continue;
+        }
+        if (sign1(r0[i]) != sign1(r1[i])) jroot[i] = (int)sign1(r1[i] - r0[i]);
+    }
+    return;
+L400:
+    if (zroot) {
+        *x = *x1;
+        for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+        for (int i = 0; i < nrt; ++i) {
+            jroot[i] = 0;
+            if (fabs(r1[i]) == 0.0) jroot[i] = (int)(-sign1(r0[i]));
+        }
+        *jflag = 3;
+        return;
+    }
+    for (int i = 0; i < nrt; ++i) rx[i] = r1[i];
+    *x = *x1;
+    *jflag = 4;
+}
+
+// DRCHEK, src/daskr.f:2494-2675.  The interpolations (ddatrp) and the y += temp2*phi(:,2) update are
+// device kernels on the internal y / yprime; rt sees device arrays and returns nrt host scalars.
+static void k_drchek(DkbCtx *c, int job, dkb_rt_t rt, int nrt, double tn, double tout, const double *psi /*1-based*/,
+                     int kold, double *r0, double *r1, double *rx, int *jroot, int *irt, double uround,
+                     double *rwork, int *iwork, double *rpar, int *ipar)
+{
+    double *RW = rwork - 1;
+    int *IW = iwork - 1;
+    const i64 neq = c->neq;
+    const int neq32 = (int)neq;
+    const double h = psi[1];
+    double t1, temp1, temp2, x = 0.0;
+    bool zroot;
+    int jflag;
+    *irt = 0;
+    for (int i = 0; i < nrt; ++i) jroot[i] = 0;
+    const double hminr = (fabs(tn) + fabs(h)) * uround * 100.0;
+
+    if (job == 1) {
+        interp(c, tn, RW[LT0], kold, psi);
+        rt(&neq32, &RW[LT0], c->y, c->yp, &nrt, r0, rpar, ipar);
+        IW[LNRTE] = 1;
+        zroot = false;
+        for (int i = 0; i < nrt; ++i)
+            if (fabs(r0[i]) == 0.0) zroot = true;
+        if (!zroot) return;
+        temp2 = std::max(hminr / fabs(h), 0.1);
+        temp1 = temp2 * h;
+        RW[LT0] = RW[LT0] + temp1;
+        v_axpy(neq, temp2, c->phi[1], c->y);
+        rt(&neq32, &RW[LT0], c->y, c->yp, &nrt, r0, rpar, ipar);
+        IW[LNRTE] = IW[LNRTE] + 1;
+        zroot = false;
+        for (int i = 0; i < nrt; ++i)
+            if (fabs(r0[i]) == 0.0) zroot = true;
+        if (zroot) *irt = -1;
+        return;
+    }
+    if (job == 2) {
+        if (IW[LIRFND] != 0) {
+            interp(c, tn, RW[LT0], kold, psi);
+            rt(&neq32, &RW[LT0], c->y, c->yp, &nrt, r0, rpar, ipar);
+            IW[LNRTE] = IW[LNRTE] + 1;
+            zroot = false;
+            for (int i = 0; i < nrt; ++i)
+                if (fabs(r0[i]) == 0.0) {
+                    zroot = true;
+                    jroot[i] = 1;
+                }
+            if (zroot) {
+                temp1 = (h >= 0.0) ? fabs(hminr) : -fabs(hminr);
+                RW[LT0] = RW[LT0] + temp1;
+                if ((RW[LT0] - tn) * h < 0.0) {
+                    interp(c, tn, RW[LT0], kold, psi);
+                } else {
+                    temp2 = temp1 / h;
+                    v_axpy(neq, temp2, c->phi[1], c->y);
+                }
+                rt(&neq32, &RW[LT0], c->y, c->yp, &nrt, r0, rpar, ipar);
+                IW[LNRTE] = IW[LNRTE] + 1;
+                for (int i = 0; i < nrt; ++i) {
+                    if (fabs(r0[i]) > 0.0) continue;
+                    if (jroot[i] == 1) {
+                        *irt = -2;
+                        return;
+                    }
+                    jroot[i] = (int)(-sign1(r0[i]));
+                    *irt = 1;
+                }
+                if (*irt == 1) return;
+            }
+        }
+        if (tn == RW[LTLAST]) return;
+    }
+    if ((tout - tn) * h >= 0.0) {
+        t1 = tn;
+    } else {
+        t1 = tout;
+        if ((t1 - RW[LT0]) * h <= 0.0) return;
+    }
+    interp(c, tn, t1, kold, psi);
+    rt(&neq32, &t1, c->y, c->yp, &nrt, r1, rpar, ipar);
+    IW[LNRTE] = IW[LNRTE] + 1;
+    jflag = 0;
+    for (;;) {
+        h_droots(nrt, hminr, &jflag, &RW[LT0], &t1, r0, r1, rx, &x, jroot);
+        if (jflag > 1) break;
+        interp(c, tn, x, kold, psi);
+        rt(&neq32, &x, c->y, c->yp, &nrt, rx, rpar, ipar);
+        IW[LNRTE] = IW[LNRTE] + 1;
+    }
+    RW[LT0] = x;
+    for (int i = 0; i < nrt; ++i) r0[i] = rx[i];
+    if (jflag == 4) return;
+    interp(c, tn, x, kold, psi);
+    *irt = 1;
+}
+
 // ---------------------------------------------------------------- DASKR
 extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, double *yprime, const double *tout_,
                           int *info, double *rtol, double *atol, int *idid, double *rwork, const int64_t *lrw,
                           int *iwork, const int64_t *liw, double *rpar, int *ipar, dkb_jack_t jac, dkb_psol_t psol,
                           void *rt, const int *nrt_, int *jroot)
 {
-    (void)rt; (void)jroot;
+    dkb_rt_t rtf = (dkb_rt_t)rt;
+    int irt = 0;
     DkbCtx *c = g_ctx;
     int *INFO = info - 1;
     if (!c) {
@@ -832,7 +1048,8 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
     if (INFO[18] < 0 || INFO[18] > 2) { why = "info(18) out of range"; goto L701; }
     if (neq <= 0) { why = "neq <= 0"; goto L701; }
     if (INFO[12] != 1) { why = "only the Krylov option info(12)=1 is implemented on device"; goto L701; }
-    if (nrt != 0) { why = "rootfinding (nrt>0) is host logic outside this path; pass nrt=0"; goto L701; }
+    if (nrt < 0) { why = "nrt < 0"; goto L701; }
+    if (nrt > 0 && rt == nullptr) { why = "nrt > 0 needs an rt routine (device arrays)"; goto L701; }
     if (INFO[10] == 1 || INFO[10] == 3) { why = "constraint checking info(10)=1,3 not implemented on device"; goto L701; }
     if (c->rbd_set && neq != (i64)c->ns * c->npts) { why = "neq does not match setup_rbdpre slab (ns*mx*myloc)"; goto L701; }
 
@@ -1058,6 +1275,11 @@ L200:
     RW[LPSI] = h;
     RW[LPSI + 1] = 2.0 * h;
     IW[LKOLD] = 1;
+    if (nrt != 0) {   // check for a zero of R near the initial T (src/daskr.f:1929-1934)
+        k_drchek(c, 1, rtf, nrt, *t, tout, &RW[LPSI - 1], IW[LKOLD], &RW[LR0], &RW[LR0 + nrt], &RW[LR0 + 2 * nrt], jroot,
+                 &irt, RW[LROUND], rwork, iwork, rpar, ipar);
+        if (irt < 0) { why = "a root function is zero at and near the initial t"; goto L701; }
+    }
     goto L500;
 
     // ---- continuation: stop tests before stepping (:1944-2042) ----
@@ -1066,6 +1288,18 @@ L400:
     done = false;
     tn = RW[LTN];
     h = RW[LH];
+    if (nrt != 0) {   // check for a zero of R near TN (src/daskr.f:1949-1963)
+        k_drchek(c, 2, rtf, nrt, tn, tout, &RW[LPSI - 1], IW[LKOLD], &RW[LR0], &RW[LR0 + nrt], &RW[LR0 + 2 * nrt], jroot,
+                 &irt, RW[LROUND], rwork, iwork, rpar, ipar);
+        if (irt < 0) { why = "root function zero at t and very close to t"; goto L701; }
+        if (irt == 1) {
+            IW[LIRFND] = 1;
+            *idid = 5;
+            *t = RW[LT0];
+            done = true;
+            goto L490;
+        }
+    }
     if (INFO[7] != 0) {
         rh = fabs(h) / RW[LHMAX];
         if (rh > 1.0) h = h / rh;
@@ -1170,7 +1404,17 @@ L500:
 L527:
     if (*idid < 0) goto L600;
 
-    // ---- successful step: stop tests (:2191-2245) ----
+    // ---- successful step: root check (:2177-2189), then stop tests (:2191-2245) ----
+    if (nrt != 0) {
+        k_drchek(c, 3, rtf, nrt, tn, tout, &RW[LPSI - 1], IW[LKOLD], &RW[LR0], &RW[LR0 + nrt], &RW[LR0 + 2 * nrt], jroot,
+                 &irt, RW[LROUND], rwork, iwork, rpar, ipar);
+        if (irt == 1) {
+            IW[LIRFND] = 1;
+            *idid = 5;
+            *t = RW[LT0];
+            goto L590;
+        }
+    }
     if (INFO[4] == 0) {
         if ((tn - tout) * h >= 0.0) {
             interp(c, tn, tout, IW[LKOLD], &RW[LPSI - 1]);

@@ -8,6 +8,7 @@
 // Compiled with -fmad=false: the reference arithmetic is separate multiply and
 // add, so elementwise results match the CPU path bit for bit.
 #include "dkb_internal.h"
+#include <cfloat>
 
 // ------------------------------------------------------------------ launch geometry
 static inline int map_grid(i64 n, int block)
@@ -309,7 +310,7 @@ __device__ __forceinline__ void block_reduce(double (&acc)[KS + KM], double *sh)
     if (wid == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            double a = (lane < nw) ? sh[lane * K + k] : 0.0;
+            double a = (lane < nw) ? sh[lane * K + k] : ((k < KS) ? 0.0 : -DBL_MAX);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 double b = __shfl_xor_sync(0xffffffffu, a, o);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(DKB_RED_BLOCK) reduce_kernel(F f, i64 n, doubl
     __shared__ int is_last;
     double acc[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int k = 0; k < K; ++k) acc[k] = (k < KS) ? 0.0 : -DBL_MAX;
     f.init();
     const i64 stride = (i64)gridDim.x * blockDim.x;
 #pragma unroll 2
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(DKB_RED_BLOCK) reduce_kernel(F f, i64 n, doubl
     if (is_last) {
         __threadfence();
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = 0.0;
+        for (int k = 0; k < K; ++k) acc[k] = (k < KS) ? 0.0 : -DBL_MAX;
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -433,6 +434,27 @@ struct RWrmsScaled {   // the reference's second pass, ddwnrm:861-864
     }
 };
 
+struct RSumStrided {   // sum of x[i*stride + off]
+    const double *x;
+    i64 stride, off;
+    __device__ void init() {}
+    __device__ void operator()(i64 i, double (&a)[1]) const { a[0] = a[0] + x[i * stride + off]; }
+};
+struct RMaxVal {
+    const double *x;
+    __device__ void init() {}
+    __device__ void operator()(i64 i, double (&a)[1]) const { a[0] = fmax(a[0], x[i]); }
+};
+void r_sum_strided(i64 npts, i64 stride, i64 off, const double *x, int slot)
+{
+    launch_reduce<1, 0>(RSumStrided{x, stride, off}, npts, slot);
+    allreduce_sum(slot, 1);
+}
+void r_max(i64 n, const double *x, int slot)
+{
+    launch_reduce<0, 1>(RMaxVal{x}, n, slot);
+    allreduce_max(slot, 1);
+}
 void r_dot(i64 n, const double *x, const double *y, int slot)
 {
     launch_reduce<1, 0>(RDot{x, y}, n, slot);

@@ -69,6 +69,10 @@ typedef void (*dkb_psol_t)(const int *neq, const double *t, const double *y,
                            int *iwp, double *b, const double *epslin, int *ierr,
                            double *rpar, int *ipar);
 
+/* root functions, src/daskr.f:908-934: rt(neq,t,y,yp,nrt,rval,rpar,ipar); y, yp device, rval host */
+typedef void (*dkb_rt_t)(const int *neq, const double *t, const double *y, const double *yp,
+                         const int *nrt, double *rval, double *rpar, int *ipar);
+
 /* ---- context (replaces the reference's SAVE/module state) ---- */
 int dkb_init(int device);            /* create the process-wide context on `device` */
 int dkb_finalize(void);
@@ -112,6 +116,9 @@ void dkb_web_psol(const int *neq, const double *t, const double *c, const double
                   const double *savr, double *wk, const double *cj, const double *wght,
                   double *rwp, int *iwp, double *b, const double *epslin, int *ierr,
                   double *rpar, int *ipar);
+/* rt, example_web.f90:600-617: rval(1) = average(c1) - 20 */
+void dkb_web_rt(const int *neq, const double *t, const double *c, const double *cdot, const int *nrt,
+                double *rval, double *rpar, int *ipar);
 /* cinit, example_web.f90:102-148: fills HOST arrays c, cdot for this rank's slab */
 int dkb_web_cinit(double *c, double *cdot, double pred_ic);
 /* heat, example/example_heat.f90:53-89 with the rbdpre ns=1 pairing of SURVEY 8(d) */
@@ -127,10 +134,12 @@ void dkb_heat_psol(const int *neq, const double *t, const double *u, const doubl
                    double *rwp, int *iwp, double *b, const double *epslin, int *ierr,
                    double *rpar, int *ipar);
 int dkb_heat_uinit(double *u, double *udot);
+/* rt, example_heat.f90:91-109: rval = max(u) - 0.1, max(u) - 0.01 */
+void dkb_heat_rt(const int *neq, const double *t, const double *u, const double *udot, const int *nrt,
+                 double *rval, double *rpar, int *ipar);
 
 /* ---- DASKR, src/daskr.f:1-3 (Krylov option info(12)=1) ----
- * Same 21 arguments.  lrw/liw are 64-bit.  rt/nrt/jroot: nrt must be 0 in this
- * version (rootfinding is host logic outside the hot path). */
+ * Same 21 arguments.  lrw/liw are 64-bit (lrw >= 60 + 3*nrt).  rt is a dkb_rt_t (or NULL with nrt = 0). */
 void dkb_daskr(dkb_res_t res, const int *neq, double *t, double *y, double *yprime,
                const double *tout, int *info, double *rtol, double *atol, int *idid,
                double *rwork, const int64_t *lrw, int *iwork, const int64_t *liw,
