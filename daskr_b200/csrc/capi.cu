@@ -512,16 +512,26 @@ void dkb_web_psol(const int *neq, const double *t, const double *cc, const doubl
                   double *wk, const double *cj, const double *wght, double *rwp, int *iwp, double *b,
                   const double *epslin, int *ierr, double *rpar, int *ipar)
 {
-    (void)neq; (void)t; (void)cc; (void)cdot; (void)savr; (void)wk; (void)cj; (void)wght; (void)epslin; (void)rpar;
+    (void)neq; (void)t; (void)cc; (void)cdot; (void)savr; (void)wght; (void)epslin; (void)rpar;
     require_problem(DKB_PROB_WEB, "dkb_web_psol");
     *ierr = 0;
-    if (ipar && (ipar[0] != 1 || ipar[1] != 0)) {
-        fprintf(stderr, "daskr_b200: only jpre=1 (reaction factor), jbg=0 is implemented on device\n");
+    // example_web.f90:346-391: jpre = ipar(1): 1 = reaction factor A_R only, 2 = spatial factor A_S only,
+    // 3 = A_S then A_R (the shipped setting), 4 = A_R then A_S; jbg = ipar(2) = 1 (block grouping) is not built
+    const int jpre = ipar ? ipar[0] : 1;
+    if (jpre < 1 || jpre > 4 || (ipar && ipar[1] != 0)) {
+        fprintf(stderr, "daskr_b200: dkb_web_psol needs jpre = ipar(1) in 1..4 and jbg = ipar(2) = 0\n");
         *ierr = -1;
         return;
     }
+    const double hl0 = 1.0 / *cj;
+    if (jpre == 2 || jpre == 3) {
+        if (web_gauss_seidel(hl0, b, wk) != 0) { *ierr = -1; return; }
+    }
     // rwp / iwp hold the blocks in the interleaved layout dkb_web_jac wrote (psol_tpp.cu)
-    tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
+    if (jpre != 2) tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
+    if (jpre == 4) {
+        if (web_gauss_seidel(hl0, b, wk) != 0) { *ierr = -1; return; }
+    }
 }
 
 void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd)

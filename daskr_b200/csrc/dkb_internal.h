@@ -204,6 +204,7 @@ int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double 
 // ---------------------------------------------------------------- problems (web.cu / heat.cu)
 void web_upload_tables();
 void web_res_launch(const double *c, const double *cdot, double *delta);
+int web_gauss_seidel(double hl0, double *z, double *x);   // gs.cu: z := GS(A_S) z, x = N words of scratch
 void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd,
                     int *d_first_flag);
 // fused datv: vnext = wscale*wt * P^-1 ( G(y + v/(wscale*wt), ydot + cj*v/(wscale*wt)) - savr )
