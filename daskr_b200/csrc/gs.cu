@@ -19,22 +19,212 @@
 
 #define GS_ITMAX 5
 #define GS_TX 32
+#define GS_U 8    // tile rows whose loads are in flight together
+
+#ifdef GS_DEBUG_CLOCKS
+__device__ long long gs_dbg[256 * 8];   // phase clocks of one CTA per launch
+#define GS_CLK(k) if (dbg) dbgp[k] = clock64()
+#else
+#define GS_CLK(k)
+#endif
 
 struct GsArgs {
-    int ns, mx, my, ty, ntx, nty;
+    int mx, my, ty, ntx, nty;
     i64 mxns;
     double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];   // beta2 = 2*beta1, gamma2 = 2*gamma1 (:452-455)
 };
 
-__global__ void __launch_bounds__(1024) gs_step_kernel(const __grid_constant__ GsArgs a, int t, double *__restrict__ z,
-                                                       double *__restrict__ x)
+// One tile of one iteration.  IT1: first iteration (x = dinv*z, no U step, z := 0 + x).
+// Shared memory: (ty+1) rows x PITCH doubles; row 0 / point column 0 = lower / left halo.  PITCH = 33*NS + 1: the odd
+// pad makes the skewed accesses of phase B (row s-lane, column lane) hit 32 different banks.
+template <int NS, int SPC, bool IT1>
+__device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, double *__restrict__ z,
+                                        double *__restrict__ x, double *sm, int t)
 {
-    extern __shared__ double sm[];   // (ty+1) rows x (GS_TX+1) columns x ns; row 0 / column 0 = lower / left halo
-    const int ns = a.ns, mx = a.mx, my = a.my;
+#ifdef GS_DEBUG_CLOCKS
+    const bool dbg = blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && t < 256;
+    long long *const dbgp = gs_dbg + (t & 255) * 8;
+#endif
+    GS_CLK(0);
+    constexpr int PITCH = (GS_TX + 1) * SPC + 1;
+    constexpr int UA = GS_U, UC = GS_U;   // g0 = first species of this CTA's group of SPC species
+    const int mx = a.mx, my = a.my;
     const i64 mxns = a.mxns;
+    const int tid = threadIdx.x;
+    const int jx0 = I * GS_TX, jy0 = J * a.ty;
+    const int w = min(GS_TX, mx - jx0), hgt = min(a.ty, my - jy0);
+    const int rtop = my - 1 - jy0;                      // tile row that is the last mesh row (>= hgt: not in this tile)
+    const bool edge = rtop < hgt;
 
-    // ---- which (iteration, tile) is this CTA? ----
-    int b = blockIdx.x, iter = 0, I = 0, J = 0;
+    // Phases A and C: thread tid < w*NS owns offset tid of every tile row (a tile row is w*NS contiguous doubles
+    // of the mesh row).  Loads are unconditional and issued GS_U rows at a time.
+    const int q = tid / SPC, i = tid - q * SPC;
+    const bool mine = tid < w * SPC;
+    const int ic = mine ? i : 0;
+    const int jx = jx0 + (mine ? q : 0) + 1;            // 1-based mesh column, as in the reference
+    const i64 col0 = (i64)jy0 * mxns + (i64)(jx - 1) * NS + g0 + ic;   // this thread's unknown in tile row 0
+    double *const smp = sm + PITCH + SPC + tid;                    // ... and its shared-memory slot
+
+    // ---- phase A: right-hand side of the triangular solve for every point of the tile, and the halos ----
+    {
+        // halo loads first (into registers): in flight together with the first batch
+        double hl[2] = {0.0, 0.0}, hb = 0.0;                       // left halo: up to 64 rows = 2 per thread
+        const bool has_hb = jy0 > 0 && mine;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)                               // this iteration's values of the left tile
+            if (jx0 > 0 && q + 32 * k < hgt) hl[k] = x[(i64)(jy0 + q + 32 * k) * mxns + (i64)(jx0 - 1) * NS + g0 + i];
+        if (has_hb) hb = x[col0 - mxns];                          // ... and of the tile below
+
+        const double b1 = a.beta1[g0 + ic], g1 = a.gamma1[g0 + ic], dinv = a.dinv[g0 + ic];
+        const double betU = (jx == 1) ? 2 * b1 : b1;              // (D-inverse)*U*x (:486-530)
+        const bool has_right = jx < mx;
+        const double *src = IT1 ? z + col0 : x + col0 + (has_right ? NS : 0);   // clamped: no right neighbour at jx == mx
+        const i64 upo = mxns - (has_right ? NS : 0);              // from src to the upper neighbour of this point
+        int r0 = 0;
+        for (; r0 + UA <= hgt; r0 += UA, src += UA * mxns) {
+            double v1[UA], v2[UA];
+#pragma unroll
+            for (int u = 0; u < UA; ++u) {
+                v1[u] = src[u * mxns];
+                if (!IT1) v2[u] = src[u * mxns + ((edge && r0 + u == rtop) ? 0 : upo)];   // no row above the last one
+            }
+#pragma unroll
+            for (int u = 0; u < UA; ++u) {
+                double uu;
+                if (IT1) {
+                    uu = dinv * v1[u];                            // x = dinv*z (:470-481)
+                } else {
+                    const double gam = (r0 + u == 0 && jy0 == 0) ? 2 * g1 : g1;
+                    const double t1 = betU * v1[u], t2 = gam * v2[u];
+                    const bool lasty = edge && r0 + u == rtop;
+                    uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
+                }
+                if (mine) smp[(r0 + u) * PITCH] = uu;
+            }
+        }
+        for (; r0 < hgt; ++r0, src += mxns) {                     // rows of a partial last batch
+            const double v1 = src[0];
+            double uu;
+            if (IT1) {
+                uu = dinv * v1;
+            } else {
+                const bool lasty = r0 == rtop;
+                const double v2 = src[lasty ? 0 : upo];
+                const double gam = (r0 == 0 && jy0 == 0) ? 2 * g1 : g1;
+                const double t1 = betU * v1, t2 = gam * v2;
+                uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
+            }
+            if (mine) smp[r0 * PITCH] = uu;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (jx0 > 0 && q + 32 * k < hgt) sm[(q + 32 * k + 1) * PITCH + i] = hl[k];
+        if (has_hb) sm[SPC + tid] = hb;
+    }
+
+    GS_CLK(1);
+    // z of the first UC rows for phase C: in flight while phase B runs
+    double zin0[UC];
+#pragma unroll
+    for (int u = 0; u < UC; ++u) zin0[u] = IT1 ? 0.0 : z[col0 + min(u, hgt - 1) * mxns];
+    __syncthreads();
+    GS_CLK(2);
+
+    // ---- phase B: [(I - (D-inverse)*L)]-inverse (:532-566) ----
+    // Warp = species, lane = tile column.  At step s lane q updates tile row s-q: its lower neighbour is its own
+    // previous result (a register); its left neighbour is what lane q-1 stored one step earlier (lane 0: the halo
+    // column).  The species are independent, so the warps never synchronise with each other.
+    {
+        const int lane = tid & 31, sp = tid >> 5;                 // blockDim = 32*SPC
+        const int jxb = jx0 + lane + 1;
+        const double b1 = a.beta1[g0 + sp], g1 = a.gamma1[g0 + sp];
+        const double bet = (jxb == mx) ? 2 * b1 : b1;
+        const bool has_left = jxb != 1;
+        const unsigned nrow = (lane < w) ? (unsigned)hgt : 0u;    // rows this lane works on
+        double *p = sm + PITCH + (lane + 1) * SPC + sp;           // row 0 of this lane's column
+        double below = p[-PITCH];                                 // lower halo (unused when jy0 == 0)
+        const int nsteps = w + hgt - 1;
+        if (edge || jy0 == 0) {
+            // tiles with mesh row 1 (no lower neighbour) or the last mesh row (gamma2)
+            const int r_nob = (jy0 == 0) ? 0 : -1;
+            for (int s = 0; s < nsteps; ++s) {
+                const int r = s - lane;
+                if ((unsigned)r < nrow) {
+                    double v = *p;
+                    const double left = p[-SPC];
+                    const double gam = (r == rtop) ? 2 * g1 : g1;
+                    if (has_left) v = v + bet * left;
+                    if (r != r_nob) v = v + gam * below;
+                    *p = v;
+                    p += PITCH;
+                    below = v;
+                }
+                __syncwarp();
+            }
+        } else {
+#pragma unroll 4
+            for (int s = 0; s < nsteps; ++s) {
+                if ((unsigned)(s - lane) < nrow) {
+                    double v = *p;
+                    const double left = p[-SPC];
+                    if (has_left) v = v + bet * left;
+                    v = v + g1 * below;
+                    *p = v;
+                    p += PITCH;
+                    below = v;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    GS_CLK(3);
+    __syncthreads();
+    GS_CLK(4);
+
+    // ---- phase C: x out, z := z + x (:568-570; z was zeroed before the first iteration, :478) ----
+    {
+        double *xo = x + col0, *zo = z + col0;
+        const double *sp = smp;
+        int r0 = 0;
+        for (; r0 + UC <= hgt; r0 += UC, xo += UC * mxns, zo += UC * mxns, sp += UC * PITCH) {
+            double zin[UC];
+            const bool more = !IT1 && r0 + UC < hgt;            // prefetch the next batch of z before storing this one
+#pragma unroll
+            for (int u = 0; u < UC; ++u) zin[u] = more ? zo[min(UC + u, hgt - 1 - r0) * mxns] : 0.0;
+            if (mine) {
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    const double v = sp[u * PITCH];
+                    xo[u * mxns] = v;
+                    zo[u * mxns] = zin0[u] + v;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) zin0[u] = zin[u];
+        }
+        if (mine) {
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                if (r0 + u < hgt) {
+                    const double v = sp[u * PITCH];
+                    xo[u * mxns] = v;
+                    zo[u * mxns] = zin0[u] + v;
+                }
+            }
+        }
+    }
+    GS_CLK(5);
+}
+
+template <int NS, int SPC>
+__global__ void __launch_bounds__(32 * SPC) gs_step_kernel(const __grid_constant__ GsArgs a, int t, double *__restrict__ z,
+                                                           double *__restrict__ x)
+{
+    extern __shared__ double sm[];
+    // ---- which (iteration, tile, species group) is this CTA? ----
+    constexpr int NG = NS / SPC;
+    const int g0 = (blockIdx.x % NG) * SPC;
+    int b = blockIdx.x / NG, iter = 0, I = 0, J = 0;
     for (int k = 0; k < GS_ITMAX; ++k) {
         const int d = t - 2 * k;
         if (d < 0 || d > a.ntx + a.nty - 2) continue;
@@ -49,78 +239,29 @@ __global__ void __launch_bounds__(1024) gs_step_kernel(const __grid_constant__ G
         b -= cnt;
     }
     if (iter == 0) return;
-    const int jx0 = I * GS_TX, jy0 = J * a.ty;
-    const int w = min(GS_TX, mx - jx0), hgt = min(a.ty, my - jy0);
-    const int pitch = (GS_TX + 1) * ns;
-    const int wns = w * ns;
-
-    // ---- phase A: right-hand side of the triangular solve for every point of the tile, and the halos ----
-    for (int e = threadIdx.x; e < hgt * wns; e += blockDim.x) {
-        const int r = e / wns, rem = e - r * wns;
-        const int q = rem / ns, i = rem - q * ns;
-        const int jx = jx0 + q + 1, jy = jy0 + r + 1;   // 1-based mesh indices, as in the reference
-        const i64 idx = (i64)(jy - 1) * mxns + (i64)(jx - 1) * ns + i;
-        double u;
-        if (iter == 1) {
-            u = a.dinv[i] * z[idx];                      // x = dinv*z (:470-481)
-        } else {                                         // (D-inverse)*U*x (:486-530)
-            const double gam = (jy == 1) ? 2 * a.gamma1[i] : a.gamma1[i];
-            const bool lasty = (jy == my);
-            if (jx == 1) {
-                const double b2 = 2 * a.beta1[i];
-                u = lasty ? b2 * x[idx + ns] : b2 * x[idx + ns] + gam * x[idx + mxns];
-            } else if (jx < mx) {
-                u = lasty ? a.beta1[i] * x[idx + ns] : a.beta1[i] * x[idx + ns] + gam * x[idx + mxns];
-            } else {
-                u = lasty ? 0.0 : gam * x[idx + mxns];
-            }
-        }
-        sm[(r + 1) * pitch + (q + 1) * ns + i] = u;
-    }
-    if (jx0 > 0)   // left halo: this iteration's values of the tile to the left
-        for (int e = threadIdx.x; e < hgt * ns; e += blockDim.x) {
-            const int r = e / ns, i = e - r * ns;
-            sm[(r + 1) * pitch + i] = x[(i64)(jy0 + r) * mxns + (i64)(jx0 - 1) * ns + i];
-        }
-    if (jy0 > 0)   // lower halo
-        for (int e = threadIdx.x; e < wns; e += blockDim.x) sm[ns + e] = x[(i64)(jy0 - 1) * mxns + (i64)jx0 * ns + e];
-    __syncthreads();
-
-    // ---- phase B: [(I - (D-inverse)*L)]-inverse (:532-566), wavefront over the tile's anti-diagonals ----
-    {
-        const int q = threadIdx.x / ns, i = threadIdx.x - q * ns;
-        const bool mine = threadIdx.x < wns;
-        const int jx = jx0 + q + 1;
-        const double bet = (jx == mx) ? 2 * a.beta1[mine ? i : 0] : a.beta1[mine ? i : 0];
-        const double g1 = a.gamma1[mine ? i : 0];
-        for (int s = 0; s < w + hgt - 1; ++s) {
-            const int r = s - q;
-            if (mine && r >= 0 && r < hgt) {
-                const int jy = jy0 + r + 1;
-                double *own = &sm[(r + 1) * pitch + (q + 1) * ns + i];
-                if (!(jy == 1 && jx == 1)) {
-                    const double gam = (jy == my) ? 2 * g1 : g1;
-                    double v = *own;
-                    if (jy == 1) v = v + bet * own[-ns];
-                    else if (jx == 1) v = v + gam * own[-pitch];
-                    else v = (v + bet * own[-ns]) + gam * own[-pitch];
-                    *own = v;
-                }
-            }
-            __syncthreads();
-        }
-    }
-
-    // ---- phase C: x out, z := z + x (:568-570; z was zeroed before the first iteration, :478) ----
-    for (int e = threadIdx.x; e < hgt * wns; e += blockDim.x) {
-        const int r = e / wns, rem = e - r * wns;
-        const i64 idx = (i64)(jy0 + r) * mxns + (i64)jx0 * ns + rem;
-        const double v = sm[(r + 1) * pitch + ns + rem];
-        x[idx] = v;
-        const double zin = (iter == 1) ? 0.0 : z[idx];
-        z[idx] = zin + v;
-    }
+    if (iter == 1) gs_tile<NS, SPC, true>(a, I, J, g0, z, x, sm, t);
+    else gs_tile<NS, SPC, false>(a, I, J, g0, z, x, sm, t);
 }
+
+template <int NS, int SPC>
+static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, cudaStream_t st)
+{
+    const size_t smem = ((size_t)(GS_TX + 1) * SPC + 1) * sizeof(double) * (a.ty + 1);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(gs_step_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
+    gs_step_kernel<NS, SPC><<<ntile * (NS / SPC), 32 * SPC, smem, st>>>(a, t, z, x);
+}
+
+// Tuning notes (1024x1024x20, B200).  A time step of the sweep costs ~20 us whatever the number of tiles in it:
+// the critical path of ONE tile is 4 dependent rounds of loads (phase A), 63 wavefront steps of ~170 clk (phase B:
+// LDS -> DMUL -> DADD -> DADD -> STS, ~25-30 clk each) and 4 rounds of stores (phase C).  Tried without gain:
+// splitting a tile's species over 2 or 4 CTAs (SPC < NS; 40- or 80-byte runs waste sectors), 16- and 32-row load
+// batches (register pressure), 16- and 64-row tiles (more launches / longer wavefronts).  What would help is
+// pipelining tiles of a column strip inside a persistent CTA; not done in this round.
+static int gs_spc(int ns) { return ns; }
 
 // z := (approximately) A_S^-1 z, x = N words of scratch.  Single rank only: the sweep order couples the slabs.
 int web_gauss_seidel(double hl0, double *z, double *x)
@@ -128,10 +269,8 @@ int web_gauss_seidel(double hl0, double *z, double *x)
     DkbCtx *c = g_ctx;
     const WebPar &wp = c->web;
     if (c->nranks > 1) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor (jpre = 2, 3, 4) is single-GPU in this version");
-    if (wp.ns > DKB_NS_MAX || GS_TX * wp.ns > 1024)
-        return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor: ns = %d too large (ns <= %d)", wp.ns, 1024 / GS_TX);
+    if (wp.ns > DKB_NS_MAX || (wp.ns & 1)) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor: ns = %d (even, <= %d)", wp.ns, DKB_NS_MAX);
     GsArgs a;
-    a.ns = wp.ns;
     a.mx = wp.mx;
     a.my = wp.my;
     a.mxns = (i64)wp.mx * wp.ns;
@@ -141,32 +280,41 @@ int web_gauss_seidel(double hl0, double *z, double *x)
         a.gamma1[i] = hl0 * wp.coy[i] * elamda;
         a.dinv[i] = elamda;
     }
-    // tile height from the shared-memory budget (200 KB of the 227 KB per CTA)
-    const size_t colbytes = (size_t)(GS_TX + 1) * wp.ns * sizeof(double);
-    int ty = (int)std::min<size_t>(32, (200u * 1024u) / colbytes - 1);
+    const int spc = gs_spc(wp.ns);
+    // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
+    const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
+    int ty = (int)std::min<size_t>(32, (200u * 1024u) / rowbytes - 1);
     ty = std::max(1, std::min(ty, wp.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
     a.nty = (wp.my + ty - 1) / ty;
-    const size_t smem = colbytes * (ty + 1);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(gs_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
-    }
-    const int threads = std::min(1024, ((std::min(GS_TX, wp.mx) * wp.ns + 31) / 32) * 32);
     const int ndiag = a.ntx + a.nty - 1;
     for (int t = 0; t < ndiag + 2 * (GS_ITMAX - 1); ++t) {
-        int nblk = 0;
+        int ntile = 0;
         for (int k = 0; k < GS_ITMAX; ++k) {
             const int d = t - 2 * k;
             if (d < 0 || d > ndiag - 1) continue;
-            nblk += std::min(a.ntx - 1, d) - std::max(0, d - (a.nty - 1)) + 1;
+            ntile += std::min(a.ntx - 1, d) - std::max(0, d - (a.nty - 1)) + 1;
         }
-        if (nblk == 0) continue;
-        gs_step_kernel<<<nblk, threads, smem, c->stream>>>(a, t, z, x);
+        if (ntile == 0) continue;
+#define GS_GO(n, sp) gs_launch<n, sp>(a, ntile, t, z, x, c->stream)
+#define GS_CASE(n) case n: GS_GO(n, n); break;
+        switch (wp.ns) {
+            GS_CASE(2) GS_CASE(4) GS_CASE(6) GS_CASE(8) GS_CASE(10) GS_CASE(12) GS_CASE(14) GS_CASE(16)
+            GS_CASE(18) GS_CASE(20) GS_CASE(22) GS_CASE(24) GS_CASE(26) GS_CASE(28) GS_CASE(30) GS_CASE(32)
+        }
+#undef GS_GO
+#undef GS_CASE
         COUNT_LAUNCH();
     }
     dkb_cuda_check("web_gauss_seidel");
     return 0;
 }
+
+#ifdef GS_DEBUG_CLOCKS
+extern "C" void dkb_debug_gs_clocks(long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, gs_dbg, sizeof(long long) * 256 * 8);
+}
+#endif

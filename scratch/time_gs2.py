@@ -1,0 +1,33 @@
+import ctypes as C, time, sys
+import numpy as np
+sys.path.insert(0, '.')
+import daskr_b200 as dk
+from daskr_b200.api import DeviceBuffer, _ref
+dk.init(0)
+L = dk.lib()
+np_, mx, my = 10, 1024, 1024
+ns = 2 * np_
+iw = np.zeros(64, dtype=np.int32)
+dk.setup_rbdpre(mx, my, ns, np_, 0, iw)
+dk.web_setpar(np_, mx, my)
+b = np.random.default_rng(0).standard_normal(ns * mx * my)
+d_b, d_wk = DeviceBuffer.from_host(b), DeviceBuffer(b.nbytes)
+neq, t, cjc, eps, ierr = C.c_int(b.size), C.c_double(0), C.c_double(1e5), C.c_double(0), C.c_int(0)
+ipar = np.array([2, 0], dtype=np.int32)
+def call():
+    L.dkb_web_psol(_ref(neq), _ref(t), None, None, None, d_wk.ptr, _ref(cjc), None, None, None, d_b.ptr, _ref(eps),
+                   _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+for _ in range(3): call()
+L.dkb_sync()
+t0 = time.perf_counter()
+for _ in range(20): call()
+L.dkb_sync()
+print("GS 1024x1024x20: %.3f ms per application" % ((time.perf_counter() - t0) / 20 * 1e3))
+import ctypes
+if hasattr(L, "dkb_debug_gs_clocks"):
+    out = (ctypes.c_longlong * 2048)()
+    call(); L.dkb_debug_gs_clocks(out)
+    v = list(out)
+    for t in (0, 2, 10, 20, 35, 50, 60, 70):
+        w = v[t*8:t*8+6]
+        print("launch %d: A %d  zin-issue+sync %d  B %d  sync %d  C %d  total %d cycles" % (t, w[1]-w[0], w[2]-w[1], w[3]-w[2], w[4]-w[3], w[5]-w[4], w[5]-w[0]))
