@@ -205,7 +205,8 @@ def run_ours(args):
     neq_g = ns * mx * my
     iwork = np.zeros(40 + neq, dtype=np.int32)
     dk.setup_rbdpre(mx, my, ns, NP_SPECIES, 40, iwork)
-    dk.web_setpar(NP_SPECIES, mx, my, ay=float(world))   # N unit squares stacked in y: same mesh spacing per GPU
+    ay = float(world) if args.ay is None else float(args.ay)
+    dk.web_setpar(NP_SPECIES, mx, my, ay=ay)   # default: N unit squares stacked in y, same mesh spacing per GPU
     stream = torch.cuda.ExternalStream(dk.lib().dkb_stream())
 
     def barrier():
@@ -219,7 +220,7 @@ def run_ours(args):
     info[10] = 1; info[11] = 1; info[13] = 1; info[14] = 1; info[15] = 1
     rwork = np.zeros(60)
     rpar = np.zeros(1)
-    ipar = np.array([1, 0], dtype=np.int32)
+    ipar = np.array([args.jpre, 0], dtype=np.int32)
     # pinned host state
     c_t = torch.empty(neq, dtype=torch.float64).pin_memory()
     cd_t = torch.empty(neq, dtype=torch.float64).pin_memory()
@@ -411,18 +412,21 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": "gmres_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak" if args.ay is None else "strong",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {
                 "workload": "food-web DAE ns=20 (np=10), %dx%d mesh (%d rows per GPU), drbdpre block-diagonal "
-                            "preconditioner, rtol=atol=1e-5, IC calculation on, tout=1 (BASELINE configs[1]%s)"
-                            % (mx, my, myloc, "" if world == 1 else ", grown along y for weak scaling; value in 1024x1024-mesh equivalents"),
-                "neq_global": neq_g, "gmres": "MAXL=5 KMP=5 NRMAX=5 EPLI=0.05 (DASKR defaults)",
+                            "preconditioner, rtol=atol=1e-5, IC calculation on, tout=1 (BASELINE configs[%d]%s)"
+                            % (mx, my, myloc, 3 if (mx == 4096 and my == 4096) else 1,
+                               "" if (world == 1 and mx == MX) else "; value in 1024x1024-mesh equivalents"
+                               + (", mesh grown along y for weak scaling" if args.ay is None and world > 1 else "")),
+                "neq_global": neq_g, "domain": "[0,1]x[0,%g]" % ay, "jpre": args.jpre, "gmres": "MAXL=5 KMP=5 NRMAX=5 EPLI=0.05 (DASKR defaults)",
                 "l2": "inputs larger than L2: %.0f MB per length-N vector, %.2f GB of LU blocks streamed per Krylov iteration" % (8 * neq / 1e6, 8.0 * ns * neq / 1e9),
                 "window": "steps %d..%d after the IC calculation, t_end=%.3e" % (W + 1, W + K, t_end_window),
                 "counters": dcount,
             },
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "phase_ms": phase_ms,
+            "nli_per_s": dnli / (ms * 1e-3), "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "phase_ms": phase_ms,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -441,6 +445,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mx", type=int, default=MX)
     ap.add_argument("--my-per-gpu", type=int, default=MY_PER_GPU)
+    ap.add_argument("--ay", type=float, default=None,
+                    help="domain height (default N: N unit squares stacked in y = weak scaling; 1 = the unit square split "
+                         "into slabs, e.g. --mx 4096 --my-per-gpu 512 --ay 1 at N=8 is BASELINE configs[3])")
+    ap.add_argument("--jpre", type=int, default=1, help="food-web preconditioner: 1 = drbdpre (configs[1]); 3 = as shipped")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-mesh", type=int, default=None)
     args = ap.parse_args()

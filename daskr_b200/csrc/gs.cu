@@ -29,7 +29,8 @@ __device__ long long gs_dbg[256 * 8];   // phase clocks of one CTA per launch
 #endif
 
 struct GsArgs {
-    int mx, my, ty, ntx, nty;
+    int mx, my, ty, ntx, nty;   // my = rows of this rank's slab
+    int bot_bnd, top_bnd;       // the slab's first / last row is a domain boundary (mirror coefficient gamma2)
     i64 mxns;
     double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];   // beta2 = 2*beta1, gamma2 = 2*gamma1 (:452-455)
 };
@@ -94,7 +95,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
                 if (IT1) {
                     uu = dinv * v1[u];                            // x = dinv*z (:470-481)
                 } else {
-                    const double gam = (r0 + u == 0 && jy0 == 0) ? 2 * g1 : g1;
+                    const double gam = (r0 + u == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
                     const double t1 = betU * v1[u], t2 = gam * v2[u];
                     const bool lasty = edge && r0 + u == rtop;
                     uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
@@ -110,7 +111,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             } else {
                 const bool lasty = r0 == rtop;
                 const double v2 = src[lasty ? 0 : upo];
-                const double gam = (r0 == 0 && jy0 == 0) ? 2 * g1 : g1;
+                const double gam = (r0 == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
                 const double t1 = betU * v1, t2 = gam * v2;
                 uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
             }
@@ -152,7 +153,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
                 if ((unsigned)r < nrow) {
                     double v = *p;
                     const double left = p[-SPC];
-                    const double gam = (r == rtop) ? 2 * g1 : g1;
+                    const double gam = (r == rtop && a.top_bnd) ? 2 * g1 : g1;
                     if (has_left) v = v + bet * left;
                     if (r != r_nob) v = v + gam * below;
                     *p = v;
@@ -263,16 +264,22 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 // pipelining tiles of a column strip inside a persistent CTA; not done in this round.
 static int gs_spc(int ns) { return ns; }
 
-// z := (approximately) A_S^-1 z, x = N words of scratch.  Single rank only: the sweep order couples the slabs.
+// z := (approximately) A_S^-1 z, x = N words of scratch.
+// Several ranks: the lexicographic sweep would run through the slabs one after the other (its length in time
+// steps does not shrink with the number of GPUs), so each rank sweeps its own slab and the coupling across the 1-row
+// slab interfaces is dropped from the preconditioner (block Jacobi over slabs, Gauss-Seidel inside).  That is a
+// different -- marginally weaker -- preconditioner than the single-GPU one: results agree to the integration
+// tolerance, not bit for bit, and iteration counts may differ by a few.
 int web_gauss_seidel(double hl0, double *z, double *x)
 {
     DkbCtx *c = g_ctx;
     const WebPar &wp = c->web;
-    if (c->nranks > 1) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor (jpre = 2, 3, 4) is single-GPU in this version");
     if (wp.ns > DKB_NS_MAX || (wp.ns & 1)) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor: ns = %d (even, <= %d)", wp.ns, DKB_NS_MAX);
     GsArgs a;
     a.mx = wp.mx;
-    a.my = wp.my;
+    a.my = c->my;
+    a.bot_bnd = (c->jy0 == 0);
+    a.top_bnd = (c->jy0 + c->my == wp.my);
     a.mxns = (i64)wp.mx * wp.ns;
     for (int i = 0; i < wp.ns; ++i) {   // :447-457
         const double elamda = 1.0 / (1.0 + 2 * hl0 * (wp.cox[i] + wp.coy[i]));
@@ -283,11 +290,16 @@ int web_gauss_seidel(double hl0, double *z, double *x)
     const int spc = gs_spc(wp.ns);
     // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
     const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
-    int ty = (int)std::min<size_t>(32, (200u * 1024u) / rowbytes - 1);
-    ty = std::max(1, std::min(ty, wp.my));
+    static int ty_knob = -1;   // DKB_GS_TY: tile-height override for tuning runs
+    if (ty_knob < 0) {
+        const char *e = getenv("DKB_GS_TY");
+        ty_knob = e ? std::max(1, std::min(32, atoi(e))) : 0;
+    }
+    int ty = (int)std::min<size_t>(ty_knob ? ty_knob : 32, (200u * 1024u) / rowbytes - 1);
+    ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
-    a.nty = (wp.my + ty - 1) / ty;
+    a.nty = (a.my + ty - 1) / ty;
     const int ndiag = a.ntx + a.nty - 1;
     for (int t = 0; t < ndiag + 2 * (GS_ITMAX - 1); ++t) {
         int ntile = 0;

@@ -5,7 +5,9 @@ import daskr_b200 as dk
 from daskr_b200.api import DeviceBuffer, _ref
 dk.init(0)
 L = dk.lib()
-np_, mx, my = 10, 1024, 1024
+import os
+M = int(os.environ.get('GS_MESH', '1024'))
+np_, mx, my = 10, M, M
 ns = 2 * np_
 iw = np.zeros(64, dtype=np.int32)
 dk.setup_rbdpre(mx, my, ns, np_, 0, iw)
@@ -22,12 +24,4 @@ L.dkb_sync()
 t0 = time.perf_counter()
 for _ in range(20): call()
 L.dkb_sync()
-print("GS 1024x1024x20: %.3f ms per application" % ((time.perf_counter() - t0) / 20 * 1e3))
-import ctypes
-if hasattr(L, "dkb_debug_gs_clocks"):
-    out = (ctypes.c_longlong * 2048)()
-    call(); L.dkb_debug_gs_clocks(out)
-    v = list(out)
-    for t in (0, 2, 10, 20, 35, 50, 60, 70):
-        w = v[t*8:t*8+6]
-        print("launch %d: A %d  zin-issue+sync %d  B %d  sync %d  C %d  total %d cycles" % (t, w[1]-w[0], w[2]-w[1], w[3]-w[2], w[4]-w[3], w[5]-w[4], w[5]-w[0]))
+print("GS %dx%dx20: %%.3f ms per application" % (mx, my) % ((time.perf_counter() - t0) / 20 * 1e3))
