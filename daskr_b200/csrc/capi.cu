@@ -121,6 +121,22 @@ static void halo_exchange_n(double *const *vecs, int nv)
     nccl_check(N.GroupEnd(), "halo group");
 }
 void halo_exchange(double *vec) { halo_exchange_n(&vec, 1); }
+void slab_overlap_exchange(const double *own, i64 n_own, i64 n_up, i64 n_down, double *from_below, double *from_above)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return;
+    ProfScope ps(PROF_HALO);
+    nccl_check(N.GroupStart(), "overlap group");
+    if (c->rank > 0) {
+        nccl_check(N.Send(own, n_down, NCCL_F64, c->rank - 1, c->comm, c->stream), "overlap send lo");
+        nccl_check(N.Recv(from_below, n_up, NCCL_F64, c->rank - 1, c->comm, c->stream), "overlap recv lo");
+    }
+    if (c->rank < c->nranks - 1) {
+        nccl_check(N.Send(own + n_own - n_up, n_up, NCCL_F64, c->rank + 1, c->comm, c->stream), "overlap send hi");
+        nccl_check(N.Recv(from_above, n_down, NCCL_F64, c->rank + 1, c->comm, c->stream), "overlap recv hi");
+    }
+    nccl_check(N.GroupEnd(), "overlap group");
+}
 void halo_exchange3(double *a, double *b, double *cc)
 {
     double *v[3] = {a, b, cc};
@@ -223,6 +239,8 @@ int dkb_finalize(void)
     cudaFree(c->d_rtol);
     cudaFree(c->d_atol);
     cudaFree(c->d_sx);
+    cudaFree(c->gs_z);
+    cudaFree(c->gs_x);
     cudaFree(c->d_scal);
     cudaFree(c->d_part);
     cudaFree(c->d_ticket);

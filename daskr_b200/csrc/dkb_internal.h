@@ -92,6 +92,8 @@ struct DkbCtx {
     i64 lenwp = 0, leniwp = 0;
 
     // device scalars + pinned mirror; reduction scratch
+    double *gs_z = nullptr, *gs_x = nullptr;   // gs.cu: overlapped-slab work vectors (several ranks only)
+    i64 gs_cap = 0;
     double *d_scal = nullptr;    // DKB_NSLOT doubles
     double *h_scal = nullptr;    // pinned
     double *d_part = nullptr;    // DKB_RED_MAXGRID * 8 partials
@@ -221,6 +223,9 @@ void heat_datv_fused(const double *v, const double *wt, double wscale, const dou
 // halo exchange of one mesh row each way (K9); no-op without a communicator
 void halo_exchange(double *vec);
 void halo_exchange3(double *a, double *b, double *c);
+// overlap rows for the slab-wise Gauss-Seidel sweep: my top n_up doubles go to rank+1 (arriving in its from_below),
+// my bottom n_down doubles to rank-1 (arriving in its from_above)
+void slab_overlap_exchange(const double *own, i64 n_own, i64 n_up, i64 n_down, double *from_below, double *from_above);
 
 // ---------------------------------------------------------------- krylov.cu
 void k_dslvk(i64 neq, const double *y, double t, const double *ydot, const double *savr,

@@ -265,21 +265,57 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 static int gs_spc(int ns) { return ns; }
 
 // z := (approximately) A_S^-1 z, x = N words of scratch.
-// Several ranks: the lexicographic sweep would run through the slabs one after the other (its length in time
-// steps does not shrink with the number of GPUs), so each rank sweeps its own slab and the coupling across the 1-row
-// slab interfaces is dropped from the preconditioner (block Jacobi over slabs, Gauss-Seidel inside).  That is a
-// different -- marginally weaker -- preconditioner than the single-GPU one: results agree to the integration
-// tolerance, not bit for bit, and iteration counts may differ by a few.
+// Several ranks: the sweep is lexicographic, so slab r would have to wait for slab r-1.  Instead every rank sweeps
+// its own slab extended by GS_OV_BELOW rows of the slab below and GS_OV_ABOVE rows of the slab above (one exchange
+// of those rows of z per application) and keeps its own rows.  Why that reproduces the global sweep: the triangular
+// solve couples a point to the rows below it through paths of weight beta^k*gamma^m with beta, gamma <= 1/4, which
+// sum to at most (1/3)^m over m rows -- 5e-16 at m = 32 -- and the U step reaches one row upwards per iteration,
+// four rows in all.  Own rows agree with the single-GPU sweep to rounding (not bit for bit).
+#define GS_OV_BELOW 32
+#define GS_OV_ABOVE 8
+static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x);
+
 int web_gauss_seidel(double hl0, double *z, double *x)
 {
     DkbCtx *c = g_ctx;
     const WebPar &wp = c->web;
-    if (wp.ns > DKB_NS_MAX || (wp.ns & 1)) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor: ns = %d (even, <= %d)", wp.ns, DKB_NS_MAX);
+    if (c->nranks <= 1) return gs_sweep(hl0, c->my, true, true, z, x);
+    const i64 mxns = (i64)wp.mx * wp.ns;
+    const int my_min = wp.my / c->nranks;                    // every slab has at least this many rows
+    const int ob = std::min(GS_OV_BELOW, my_min), oa = std::min(GS_OV_ABOVE, my_min);
+    const int nb = c->rank > 0 ? ob : 0, na = c->rank < c->nranks - 1 ? oa : 0;
+    const i64 need = (i64)(nb + c->my + na) * mxns;
+    if (need > c->gs_cap) {
+        cudaFree(c->gs_z);
+        cudaFree(c->gs_x);
+        c->gs_z = c->gs_x = nullptr;
+        c->gs_cap = 0;
+        const i64 cap = (i64)(c->my + 1 + ob + oa) * mxns;
+        if (cudaMalloc(&c->gs_z, sizeof(double) * cap) != cudaSuccess || cudaMalloc(&c->gs_x, sizeof(double) * cap) != cudaSuccess)
+            return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the overlapped-slab work vectors");
+        c->gs_cap = cap;
+    }
+    const i64 n_own = (i64)c->my * mxns;
+    double *zo = c->gs_z + (i64)nb * mxns;
+    cudaMemcpyAsync(zo, z, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
+    slab_overlap_exchange(z, n_own, (i64)ob * mxns, (i64)oa * mxns, c->gs_z, zo + n_own);
+    const int rc = gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, c->gs_z, c->gs_x);
+    cudaMemcpyAsync(z, zo, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
+    (void)x;
+    return rc;
+}
+
+// The sweep over `my` rows of z (in place), x = scratch of the same size.  bot_bnd / top_bnd: the first / last row is a
+// domain boundary (mirror coefficients beta2/gamma2 as in the reference); otherwise the neighbour row is simply absent.
+static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x)
+{
+    DkbCtx *c = g_ctx;
+    const WebPar &wp = c->web;
     GsArgs a;
     a.mx = wp.mx;
-    a.my = c->my;
-    a.bot_bnd = (c->jy0 == 0);
-    a.top_bnd = (c->jy0 + c->my == wp.my);
+    a.my = my;
+    a.bot_bnd = bot_bnd;
+    a.top_bnd = top_bnd;
     a.mxns = (i64)wp.mx * wp.ns;
     for (int i = 0; i < wp.ns; ++i) {   // :447-457
         const double elamda = 1.0 / (1.0 + 2 * hl0 * (wp.cox[i] + wp.coy[i]));
