@@ -256,13 +256,24 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
     gs_step_kernel<NS, SPC><<<ntile * (NS / SPC), 32 * SPC, smem, st>>>(a, t, z, x);
 }
 
-// Tuning notes (1024x1024x20, B200).  A time step of the sweep costs ~20 us whatever the number of tiles in it:
-// the critical path of ONE tile is 4 dependent rounds of loads (phase A), 63 wavefront steps of ~170 clk (phase B:
-// LDS -> DMUL -> DADD -> DADD -> STS, ~25-30 clk each) and 4 rounds of stores (phase C).  Tried without gain:
-// splitting a tile's species over 2 or 4 CTAs (SPC < NS; 40- or 80-byte runs waste sectors), 16- and 32-row load
-// batches (register pressure), 16- and 64-row tiles (more launches / longer wavefronts).  What would help is
-// pipelining tiles of a column strip inside a persistent CTA; not done in this round.
-static int gs_spc(int ns) { return ns; }
+// Tuning notes (ns = 20, B200; profiles/README.md has the numbers).  One tile costs ~20 us on its SM whatever else
+// runs: 4 dependent rounds of loads (phase A), 63 wavefront steps of ~170 clk (phase B: LDS -> DMUL -> DADD -> DADD ->
+// STS) and 4 rounds of loads/stores (phase C), with 20 warps per SM to hide the latencies (issue slots are 1/3 used, the
+// dominant stall is long-scoreboard).  On a 1024x1024 mesh the sweep is 71 launches of <= 148 tiles, i.e. latency-bound;
+// on 4096x4096 it is 263 launches of up to 640 tiles and runs at ~2.7 TB/s of algorithmic traffic.  Tried without
+// gain: two CTAs per tile with half of the species each (same number of warps per SM), 16- and 32-row load batches
+// (register pressure at 640 threads), 16-row tiles (longer wavefront ramps, more launches).  The next step is a
+// persistent CTA per column strip with TMA double-buffered tiles, so that loads, wavefront and stores of
+// consecutive tiles overlap.
+static int gs_spc(int ns)
+{
+    static int knob = -1;   // DKB_GS_SPLIT=1: two CTAs per tile (half of the species each), tuning runs
+    if (knob < 0) {
+        const char *e = getenv("DKB_GS_SPLIT");
+        knob = e ? atoi(e) : 0;
+    }
+    return (knob == 1 && ns % 4 == 0) ? ns / 2 : ns;
+}
 
 // z := (approximately) A_S^-1 z, x = N words of scratch.
 // Several ranks: the sweep is lexicographic, so slab r would have to wait for slab r-1.  Instead every rank sweeps
@@ -331,7 +342,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         const char *e = getenv("DKB_GS_TY");
         ty_knob = e ? std::max(1, std::min(32, atoi(e))) : 0;
     }
-    int ty = (int)std::min<size_t>(ty_knob ? ty_knob : 32, (200u * 1024u) / rowbytes - 1);
+    int ty = (int)std::min<size_t>(ty_knob ? ty_knob : 32, ((spc == wp.ns ? 200u : 110u) * 1024u) / rowbytes - 1);
     ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
@@ -347,12 +358,14 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         if (ntile == 0) continue;
 #define GS_GO(n, sp) gs_launch<n, sp>(a, ntile, t, z, x, c->stream)
 #define GS_CASE(n) case n: GS_GO(n, n); break;
+#define GS_CASE2(n) case n: if (spc == n) GS_GO(n, n); else GS_GO(n, n / 2); break;
         switch (wp.ns) {
-            GS_CASE(2) GS_CASE(4) GS_CASE(6) GS_CASE(8) GS_CASE(10) GS_CASE(12) GS_CASE(14) GS_CASE(16)
-            GS_CASE(18) GS_CASE(20) GS_CASE(22) GS_CASE(24) GS_CASE(26) GS_CASE(28) GS_CASE(30) GS_CASE(32)
+            GS_CASE(2) GS_CASE2(4) GS_CASE(6) GS_CASE2(8) GS_CASE(10) GS_CASE2(12) GS_CASE(14) GS_CASE2(16)
+            GS_CASE(18) GS_CASE2(20) GS_CASE(22) GS_CASE2(24) GS_CASE(26) GS_CASE2(28) GS_CASE(30) GS_CASE2(32)
         }
 #undef GS_GO
 #undef GS_CASE
+#undef GS_CASE2
         COUNT_LAUNCH();
     }
     dkb_cuda_check("web_gauss_seidel");
