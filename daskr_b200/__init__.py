@@ -30,6 +30,10 @@ from .api import (  # noqa: F401
     HEAT_RES,
     HEAT_JAC,
     HEAT_PSOL,
+    WEB_RT,
+    HEAT_RT,
+    state_export,
+    state_import,
     dgefa_batched,
     dgesl_batched,
     solve_web,

@@ -31,7 +31,8 @@ EXPORTS = [
     "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
     "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
-    "dkb_heat_psol", "dkb_heat_uinit", "dkb_web_rt", "dkb_heat_rt", "dkb_daskr", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
+    "dkb_heat_psol", "dkb_heat_uinit", "dkb_web_rt", "dkb_heat_rt", "dkb_daskr",
+    "dkb_state_bytes", "dkb_state_export", "dkb_state_import", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
     "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
@@ -53,6 +54,9 @@ def lib():
     L.dkb_stream.restype = C.c_void_p
     L.dkb_ddwnrm.restype = C.c_double
     L.dkb_launch_count.restype = C.c_int64
+    L.dkb_state_bytes.restype = C.c_int64
+    L.dkb_state_export.argtypes = [C.c_void_p, C.c_int64]
+    L.dkb_state_import.argtypes = [C.c_void_p, C.c_int64]
     L.dkb_set_option.argtypes = [C.c_int, C.c_int64]
     L.dkb_web_cinit.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
     L.dkb_web_setpar_ex.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
@@ -118,6 +122,22 @@ def init(device=0):
 def finalize():
     if _lib is not None:
         _lib.dkb_finalize()
+
+
+def state_export():
+    """Device-side solver state (y, yprime, PHI, WP/IWP, ID, vector tolerances, SAVEd scalars) as one uint8 array.
+    Together with rwork / iwork / t this is a checkpoint (include/daskr_b200.h)."""
+    n = int(lib().dkb_state_bytes())
+    if n <= 0:
+        raise DaskrError("no solver state to export")
+    buf = np.empty(n, dtype=np.uint8)
+    _check(lib().dkb_state_export(_p(buf), n), "dkb_state_export")
+    return buf
+
+
+def state_import(buf):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    _check(lib().dkb_state_import(_p(buf), buf.size), "dkb_state_import")
 
 
 def set_option(opt, value):

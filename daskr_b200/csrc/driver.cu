@@ -792,6 +792,101 @@ static void k_ddasic(DkbCtx *c, const Cb &cb, double x, int icopt, double *h, do
     *idid = -12;
 }
 
+// ---------------------------------------------------------------- state export / import
+// The reference keeps its whole state in the caller's rwork / iwork, so a run can be checkpointed by saving those
+// arrays (plus y, yprime) and continued later with info(1) = 1.  Here the length-NEQ segments of rwork live on the
+// device; these three calls move exactly what a continuation call reads -- y, yprime, the PHI array, the
+// preconditioner blocks WP / IWP, the ID array and vector tolerances, and the SAVEd scalars -- to and from one host
+// buffer.  rwork(1:60+3*nrt) and iwork(1:40+...) stay with the caller, as in the reference.
+struct DkbStateHdr {
+    char magic[8];
+    i64 neq, neq_g, lenwp, leniwp, s_lid;
+    int maxl, kmp, has_id, has_tol, s_lenid, s_nonneg, s_ncphi, s_icnflg;
+};
+
+static i64 state_bytes(const DkbCtx *c)
+{
+    i64 n = (i64)sizeof(DkbStateHdr) + (i64)sizeof(double) * c->neq * 8 + (i64)sizeof(double) * c->lenwp +
+            (i64)sizeof(int) * c->leniwp;
+    if (c->d_id) n += (i64)sizeof(int) * c->neq;
+    if (c->d_rtol) n += (i64)sizeof(double) * c->neq * 2;
+    return n;
+}
+
+extern "C" int64_t dkb_state_bytes(void)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena) return 0;
+    return state_bytes(c);
+}
+
+extern "C" int dkb_state_export(void *buf, int64_t nbytes)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena) return dkb_fail(DKB_E_STATE, "dkb_state_export: no solver state (call dkb_daskr first)");
+    if (nbytes < state_bytes(c)) return dkb_fail(DKB_E_ARG, "dkb_state_export: buffer too small (need %lld bytes)", (long long)state_bytes(c));
+    DkbStateHdr h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "DKBSTAT1", 8);
+    h.neq = c->neq; h.neq_g = c->neq_g; h.lenwp = c->lenwp; h.leniwp = c->leniwp; h.s_lid = c->s_lid;
+    h.maxl = c->maxl; h.kmp = c->kmp; h.has_id = c->d_id != nullptr; h.has_tol = c->d_rtol != nullptr;
+    h.s_lenid = c->s_lenid; h.s_nonneg = c->s_nonneg; h.s_ncphi = c->s_ncphi; h.s_icnflg = c->s_icnflg;
+    char *p = (char *)buf;
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+    auto out = [&](const void *d, size_t n) {
+        cudaMemcpyAsync(p, d, n, cudaMemcpyDeviceToHost, c->stream);
+        p += n;
+    };
+    const size_t nb = sizeof(double) * c->neq;
+    out(c->y, nb);
+    out(c->yp, nb);
+    for (int j = 0; j < 6; ++j) out(c->phi[j], nb);
+    out(c->wp, sizeof(double) * c->lenwp);
+    out(c->iwp, sizeof(int) * c->leniwp);
+    if (c->d_id) out(c->d_id, sizeof(int) * c->neq);
+    if (c->d_rtol) { out(c->d_rtol, nb); out(c->d_atol, nb); }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// After dkb_init, dkb_setup_rbdpre and the problem's setpar (same mesh, same ranks).  The next dkb_daskr call must
+// be a continuation call (info(1) = 1) with the rwork / iwork saved next to this buffer.
+extern "C" int dkb_state_import(const void *buf, int64_t nbytes)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    DkbStateHdr h;
+    if (nbytes < (int64_t)sizeof h) return dkb_fail(DKB_E_ARG, "dkb_state_import: buffer too small");
+    memcpy(&h, buf, sizeof h);
+    if (memcmp(h.magic, "DKBSTAT1", 8) != 0) return dkb_fail(DKB_E_ARG, "dkb_state_import: not a daskr_b200 state buffer");
+    if (c->rbd_set && h.neq != (i64)c->ns * c->npts)
+        return dkb_fail(DKB_E_ARG, "dkb_state_import: state has neq = %lld, this mesh slab has %lld", (long long)h.neq,
+                        (long long)((i64)c->ns * c->npts));
+    const i64 rbd_wp = c->rbd_set ? tpp_lut_doubles(c->ns, c->npts) : 0, rbd_iwp = c->rbd_set ? tpp_pt_ints(c->ns, c->npts) : 0;
+    if (alloc_solver(c, h.neq, h.maxl, h.kmp, 0, h.has_id, 0, h.has_tol, h.lenwp - rbd_wp, h.leniwp - rbd_iwp) != 0) return DKB_E_CUDA;
+    if (c->lenwp != h.lenwp || c->leniwp != h.leniwp) return dkb_fail(DKB_E_ARG, "dkb_state_import: preconditioner storage differs");
+    c->neq_g = h.neq_g; c->s_lid = h.s_lid; c->s_lenid = h.s_lenid; c->s_nonneg = h.s_nonneg; c->s_ncphi = h.s_ncphi;
+    c->s_icnflg = h.s_icnflg;
+    i64 need = state_bytes(c);
+    if (nbytes < need) return dkb_fail(DKB_E_ARG, "dkb_state_import: buffer truncated (need %lld bytes)", (long long)need);
+    const char *p = (const char *)buf + sizeof h;
+    auto in = [&](void *d, size_t n) {
+        cudaMemcpyAsync(d, p, n, cudaMemcpyHostToDevice, c->stream);
+        p += n;
+    };
+    const size_t nb = sizeof(double) * c->neq;
+    in(c->y, nb);
+    in(c->yp, nb);
+    for (int j = 0; j < 6; ++j) in(c->phi[j], nb);
+    in(c->wp, sizeof(double) * c->lenwp);
+    in(c->iwp, sizeof(int) * c->leniwp);
+    if (c->d_id) in(c->d_id, sizeof(int) * c->neq);
+    if (c->d_rtol) { in(c->d_rtol, nb); in(c->d_atol, nb); }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // ---------------------------------------------------------------- rootfinding (DRCHEK / DROOTS)
 static inline double sign1(double x) { return signbit(x) ? -1.0 : 1.0; }   // SIGN(1.0D0, x)
 

@@ -146,6 +146,15 @@ void dkb_daskr(dkb_res_t res, const int *neq, double *t, double *y, double *ypri
                double *rpar, int *ipar, dkb_jack_t jac, dkb_psol_t psol, void *rt,
                const int *nrt, int *jroot);
 
+/* ---- checkpoint-style continuation.  The reference keeps its whole state in the caller's
+ * rwork / iwork (src/daskr.f:1424-1427, 1724-1735): saving those arrays is a checkpoint.  Here their length-NEQ
+ * segments (PHI, WP/IWP, ID ...) live on the device; these calls move them to / from one HOST buffer.  Save
+ * rwork(1:60+3*nrt), iwork and (t, idid) next to it; after dkb_init + dkb_setup_rbdpre + setpar in a new process,
+ * dkb_state_import and a continuation call (info(1) = 1) take the same steps as the uninterrupted run. */
+int64_t dkb_state_bytes(void);
+int dkb_state_export(void *host_buf, int64_t nbytes);
+int dkb_state_import(const void *host_buf, int64_t nbytes);
+
 /* ---- the hot path as separate calls (what a Fortran dnsk/dnedk would bind) ---- */
 /* dslvk, src/daskr_new.f90:3036-3165.  Device arrays y, ydot, savr, x, ewt of
  * length neq; counters are accumulated into iwm(12,16,20,21) like the reference. */
