@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     finalize,
     set_option,
     setup_rbdpre,
+    setup_rbgpre,
     slab,
     web_setpar,
     web_cinit,

@@ -28,7 +28,7 @@ PSOL_T = C.CFUNCTYPE(None, *([C.c_void_p] * 15))
 # every symbol include/daskr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "dkb_init", "dkb_finalize", "dkb_last_error", "dkb_version", "dkb_stream", "dkb_set_option", "dkb_sync",
-    "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
+    "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_setup_rbgpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
     "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
     "dkb_heat_psol", "dkb_heat_uinit", "dkb_web_rt", "dkb_heat_rt", "dkb_daskr",
@@ -166,6 +166,13 @@ def setup_rbdpre(mx, my, ns, nsd, lid, iwork):
     assert iwork.dtype == np.int32
     a = [C.c_int(int(v)) for v in (mx, my, ns, nsd, lid)]
     lib().dkb_setup_rbdpre(*[C.byref(v) for v in a], _p(iwork))
+
+
+def setup_rbgpre(mx, my, ns, nsd, nxg, nyg, lid, iwork):
+    """setup_rbgpre(mx, my, ns, nsd, nxg, nyg, lid, iwork) -- src/daskr_rbgpre.f90:107-158 (DGSET2): block grouping."""
+    assert iwork.dtype == np.int32
+    a = [C.c_int(int(v)) for v in (mx, my, ns, nsd, nxg, nyg, lid)]
+    lib().dkb_setup_rbgpre(*[C.byref(v) for v in a], _p(iwork))
 
 
 def slab():
@@ -333,13 +340,14 @@ def launch_count():
 
 # ---------------------------------------------------------------- whole-run drivers
 def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fused=True, ic=True, pred_ic=None,
-              y_out=True, roots=False):
+              y_out=True, roots=False, nxg=0, nyg=0):
     """The food-web example as example/example_web.f90:884-954 runs it (Krylov, no grouping, nrt=0):
     one DASKR call for consistent initial values (info(11)=1, info(14)=1 -> idid=4), then integration
     with outputs at `touts`.  Returns dict(y=[nout, neq], counters=[nout, 40], rhead=[nout, 60], idid, t).
     With max_steps > 0 the run stops after that many BDF steps (info(3)=1 stepping).  roots=True adds the
     example's root function (nrt=1, average(c1) - 20, example_web.f90:600-617); every idid=5 return is
-    recorded in result["roots"] as (t, jroot, counters) and the integration continues."""
+    recorded in result["roots"] as (t, jroot, counters) and the integration continues.  nxg, nyg > 0: block
+    grouping (jbg = 1, nxg x nyg groups; the example's METH = 2 uses 5 x 5, example_web.f90:873-877)."""
     ns = 2 * np_
     iwork = np.zeros(40 + 1, dtype=np.int32)  # sized below once the slab is known
     probe = np.zeros(64, dtype=np.int32)
@@ -347,7 +355,11 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     _, myloc = slab()
     neq = ns * mx * myloc
     iwork = np.zeros(40 + neq, dtype=np.int32)
-    setup_rbdpre(mx, my, ns, np_, 40, iwork)
+    jbg = 1 if nxg > 0 else 0
+    if jbg:
+        setup_rbgpre(mx, my, ns, np_, nxg, nyg, 40, iwork)
+    else:
+        setup_rbdpre(mx, my, ns, np_, 40, iwork)
     web_setpar(np_, mx, my)
     set_option(OPT_FUSED, 2 if fused is True else int(fused))   # 0 callbacks, 1 two kernels, 2 single fused kernel
     info = np.zeros(20, dtype=np.int32)
@@ -360,7 +372,7 @@ def solve_web(np_, mx, my, touts, rtol=1e-5, atol=1e-5, jpre=1, max_steps=0, fus
     found = []
     rwork = np.zeros(60 + 3 * nrt)
     rpar = np.zeros(1)
-    ipar = np.array([jpre, 0], dtype=np.int32)
+    ipar = np.array([jpre, jbg], dtype=np.int32)
     if pred_ic is None:
         pred_ic = 1e5 * np_   # example_web.f90:784 uses 1e5 for np=1 (= ee * prey level * np): start near the non-trivial branch
     c, cdot = web_cinit(neq, pred_ic)

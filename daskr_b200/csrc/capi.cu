@@ -120,6 +120,12 @@ static void halo_exchange_n(double *const *vecs, int nv)
     }
     nccl_check(N.GroupEnd(), "halo group");
 }
+void allreduce_sum_buf(double *buf, i64 n)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1 || n <= 0) return;
+    nccl_check(N.AllReduce(buf, buf, (size_t)n, NCCL_F64, NCCL_SUM, c->comm, c->stream), "allreduce_sum_buf");
+}
 void halo_exchange(double *vec) { halo_exchange_n(&vec, 1); }
 void slab_overlap_exchange(const double *own, i64 n_own, i64 n_up, i64 n_down, double *from_below, double *from_above)
 {
@@ -241,6 +247,9 @@ int dkb_finalize(void)
     cudaFree(c->d_sx);
     cudaFree(c->gs_z);
     cudaFree(c->gs_x);
+    cudaFree(c->d_jigx);
+    cudaFree(c->d_jigy);
+    cudaFree(c->d_rep);
     cudaFree(c->d_scal);
     cudaFree(c->d_part);
     cudaFree(c->d_ticket);
@@ -327,6 +336,7 @@ void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *ns
     c->halo = (i64)c->ns * c->mx;
     c->halo_pad = ((c->halo + 31) / 32) * 32;
     c->rbd_set = 1;
+    c->rbg_set = 0;
     // blocks and pivots are device resident and sized in 64 bits: nothing is carved from rwork/iwork
     int *IW = iwork - 1;
     IW[27] = 0;
@@ -339,6 +349,55 @@ void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *ns
             for (int i = c->nsd + 1; i <= c->ns; ++i) IW[i0 + i] = -1;
             i0 = i0 + c->ns;
         }
+}
+
+// set_grouping, src/daskr_rbgpre.f90:160-193 (1-based tables; jg is not needed on the device)
+static void set_grouping(int m, int ng, std::vector<int> &jig, std::vector<int> &jr)
+{
+    jig.assign(m + 1, 0);
+    jr.assign(ng + 1, 0);
+    const int mper = m / ng, ngm1 = ng - 1;
+    int len1 = ngm1 * mper;
+    for (int j = 1; j <= len1; ++j) jig[j] = 1 + (j - 1) / mper;
+    len1 = len1 + 1;
+    for (int j = len1; j <= m; ++j) jig[j] = ng;
+    for (int ig = 1; ig <= ngm1; ++ig) jr[ig] = (int)(0.5 + ((double)ig - 0.5) * mper);
+    jr[ng] = (int)(0.5 * (1 + ngm1 * mper + m));
+}
+
+// setup_rbgpre (DGSET2), src/daskr_rbgpre.f90:107-158: same arguments.  The nxg*nyg blocks and their pivots live on
+// the device (iwork(27:28) = 0 as for dkb_setup_rbdpre); on several GPUs every rank holds all of them.
+void dkb_setup_rbgpre(const int *mx, const int *my, const int *ns, const int *nsd, const int *nxg, const int *nyg,
+                      const int *lid, int *iwork)
+{
+    dkb_setup_rbdpre(mx, my, ns, nsd, lid, iwork);   // mesh, slab split, ID array: identical (:125-157)
+    DkbCtx *c = g_ctx;
+    if (*nxg < 1 || *nyg < 1 || *nxg > *mx || *nyg > *my) {
+        fprintf(stderr, "daskr_b200: dkb_setup_rbgpre: need 1 <= nxg <= mx and 1 <= nyg <= my\n");
+        abort();
+    }
+    c->ngx = *nxg;
+    c->ngy = *nyg;
+    std::vector<int> jigx, jigy, jxr, jyr;
+    set_grouping(c->mx, c->ngx, jigx, jxr);
+    set_grouping(c->my_g, c->ngy, jigy, jyr);
+    std::vector<i64> rep((size_t)c->ngx * c->ngy);
+    for (int igy = 1; igy <= c->ngy; ++igy)
+        for (int igx = 1; igx <= c->ngx; ++igx) {
+            const int jyl = jyr[igy] - 1 - c->jy0;   // local row of the representative point
+            rep[(size_t)(igy - 1) * c->ngx + igx - 1] = (jyl >= 0 && jyl < c->my) ? (i64)jyl * c->mx + (jxr[igx] - 1) : -1;
+        }
+    cudaFree(c->d_jigx);
+    cudaFree(c->d_jigy);
+    cudaFree(c->d_rep);
+    cudaMalloc(&c->d_jigx, sizeof(int) * c->mx);
+    cudaMalloc(&c->d_jigy, sizeof(int) * c->my_g);
+    cudaMalloc(&c->d_rep, sizeof(i64) * rep.size());
+    cudaMemcpy(c->d_jigx, jigx.data() + 1, sizeof(int) * c->mx, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_jigy, jigy.data() + 1, sizeof(int) * c->my_g, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_rep, rep.data(), sizeof(i64) * rep.size(), cudaMemcpyHostToDevice);
+    dkb_cuda_check("dkb_setup_rbgpre");
+    c->rbg_set = 1;
 }
 
 int dkb_slab(int *jy0, int *myloc)
@@ -514,12 +573,22 @@ void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, doub
     (void)res; (void)ires; (void)neq; (void)t; (void)cdot; (void)savr; (void)wk; (void)h; (void)rpar;
     require_problem(DKB_PROB_WEB, "dkb_web_jac");
     DkbCtx *c = g_ctx;
-    if (ipar && ipar[1] != 0) {
-        fprintf(stderr, "daskr_b200: block-grouping (jbg=1) is not implemented\n");
+    const int jbg = ipar ? ipar[1] : 0;   // example_web.f90:337-342
+    if (jbg != (c->rbg_set ? 1 : 0)) {
+        fprintf(stderr, "daskr_b200: dkb_web_jac: jbg = ipar(2) = %d needs dkb_setup_%s first\n", jbg, jbg ? "rbgpre" : "rbdpre");
         *ierr = -1;
         return;
     }
     arm_first_flag(c);
+    if (jbg == 1) {   // jac_rbgpre: blocks at the representative points, summed over ranks, then cj*I_d and dgefa
+        const int ngrp = c->ngx * c->ngy;
+        web_jac_groups_launch(cc, rewt, rwp);
+        allreduce_sum_buf(rwp, (i64)ngrp * c->ns * c->ns);
+        rbg_add_cj(rwp, c->ns, c->nsd, ngrp, *cj);
+        lu_dgefa_batched(rwp, iwp, c->ns, ngrp, nullptr, c->d_iflag + 1);
+        *ierr = fetch_first_flag(c);
+        return;
+    }
     web_jac_launch(cc, rewt, *cj, rwp, iwp, c->d_iflag + 1);
     // ierr = dgefa info of the first failing block in the reference; here its block number
     *ierr = fetch_first_flag(c);
@@ -534,10 +603,11 @@ void dkb_web_psol(const int *neq, const double *t, const double *cc, const doubl
     require_problem(DKB_PROB_WEB, "dkb_web_psol");
     *ierr = 0;
     // example_web.f90:346-391: jpre = ipar(1): 1 = reaction factor A_R only, 2 = spatial factor A_S only,
-    // 3 = A_S then A_R (the shipped setting), 4 = A_R then A_S; jbg = ipar(2) = 1 (block grouping) is not built
+    // 3 = A_S then A_R (the shipped setting), 4 = A_R then A_S; jbg = ipar(2) = 1: block grouping (dkb_setup_rbgpre)
     const int jpre = ipar ? ipar[0] : 1;
-    if (jpre < 1 || jpre > 4 || (ipar && ipar[1] != 0)) {
-        fprintf(stderr, "daskr_b200: dkb_web_psol needs jpre = ipar(1) in 1..4 and jbg = ipar(2) = 0\n");
+    const int jbg = ipar ? ipar[1] : 0;
+    if (jpre < 1 || jpre > 4 || jbg != (g_ctx->rbg_set ? 1 : 0)) {
+        fprintf(stderr, "daskr_b200: dkb_web_psol needs jpre = ipar(1) in 1..4 and jbg = ipar(2) matching the setup call\n");
         *ierr = -1;
         return;
     }
@@ -546,7 +616,10 @@ void dkb_web_psol(const int *neq, const double *t, const double *cc, const doubl
         if (web_gauss_seidel(hl0, b, wk) != 0) { *ierr = -1; return; }
     }
     // rwp / iwp hold the blocks in the interleaved layout dkb_web_jac wrote (psol_tpp.cu)
-    if (jpre != 2) tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
+    if (jpre != 2) {
+        if (jbg == 1) rbg_psol(rwp, iwp, b);   // psol_rbgpre
+        else tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
+    }
     if (jpre == 4) {
         if (web_gauss_seidel(hl0, b, wk) != 0) { *ierr = -1; return; }
     }
@@ -790,9 +863,9 @@ int dkb_debug_time_datv(int level, int variant, int reps, double *ms)
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1]);   // warm
+    web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);   // warm
     cudaEventRecord(a, c->stream);
-    for (int i = 0; i < reps; ++i) web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1]);
+    for (int i = 0; i < reps; ++i) web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);
     cudaEventRecord(b, c->stream);
     cudaEventSynchronize(b);
     float t = 0.f;

@@ -92,6 +92,11 @@ struct DkbCtx {
     i64 lenwp = 0, leniwp = 0;
 
     // device scalars + pinned mirror; reduction scratch
+    // block grouping (setup_rbgpre, src/daskr_rbgpre.f90:107-193): group of every mesh column / GLOBAL row (1-based),
+    // local point index of each group's representative point (-1: on another rank)
+    int rbg_set = 0, ngx = 0, ngy = 0;
+    int *d_jigx = nullptr, *d_jigy = nullptr;
+    i64 *d_rep = nullptr;
     double *gs_z = nullptr, *gs_x = nullptr;   // gs.cu: overlapped-slab work vectors (several ranks only)
     i64 gs_cap = 0;
     double *d_scal = nullptr;    // DKB_NSLOT doubles
@@ -206,13 +211,17 @@ int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double 
 // ---------------------------------------------------------------- problems (web.cu / heat.cu)
 void web_upload_tables();
 void web_res_launch(const double *c, const double *cdot, double *delta);
-int web_gauss_seidel(double hl0, double *z, double *x);   // gs.cu: z := GS(A_S) z, x = N words of scratch
+int web_gauss_seidel(double hl0, double *z, double *x);
+// block-grouped reaction factor (jbg = 1): FD blocks at the representative points (unfactored, reference layout)
+void web_jac_groups_launch(const double *c, const double *rewt, double *bd);
+void rbg_add_cj(double *bd, int ns, int nsd, int ngrp, double cj);
+int rbg_psol(const double *bd, const int *ipbd, double *b);
+void allreduce_sum_buf(double *buf, i64 n);   // gs.cu: z := GS(A_S) z, x = N words of scratch
 void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd,
                     int *d_first_flag);
 // fused datv: vnext = wscale*wt * P^-1 ( G(y + v/(wscale*wt), ydot + cj*v/(wscale*wt)) - savr )
-void web_datv_fused(const double *v, const double *wt, double wscale, const double *y,
-                    const double *ydot, const double *savr, double cj, const double *bd,
-                    const int *ipbd, double *vnext);
+int web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+                   const double *savr, double cj, const double *bd, const int *ipbd, double *vnext, int jpre);
 void heat_res_launch(const double *u, const double *udot, double *delta);
 void heat_jac_launch(const double *u, const double *rewt, double cj, double *bd, int *ipbd,
                      int *d_first_flag);

@@ -97,7 +97,10 @@ static int alloc_solver(DkbCtx *c, i64 neq, int maxl, int kmp, int need_vt, int 
     // for through iwork(27:28)
     {
         i64 lenwp = user_lenwp, leniwp = user_leniwp;
-        if (c->rbd_set) {   // interleaved layout pads the point count to a multiple of 32
+        if (c->rbg_set) {   // block grouping: one block per group, reference layout
+            lenwp += (i64)c->ngx * c->ngy * c->ns * c->ns;
+            leniwp += (i64)c->ngx * c->ngy * c->ns;
+        } else if (c->rbd_set) {   // interleaved layout pads the point count to a multiple of 32
             lenwp += tpp_lut_doubles(c->ns, c->npts);
             leniwp += tpp_pt_ints(c->ns, c->npts);
         }
@@ -863,7 +866,8 @@ extern "C" int dkb_state_import(const void *buf, int64_t nbytes)
     if (c->rbd_set && h.neq != (i64)c->ns * c->npts)
         return dkb_fail(DKB_E_ARG, "dkb_state_import: state has neq = %lld, this mesh slab has %lld", (long long)h.neq,
                         (long long)((i64)c->ns * c->npts));
-    const i64 rbd_wp = c->rbd_set ? tpp_lut_doubles(c->ns, c->npts) : 0, rbd_iwp = c->rbd_set ? tpp_pt_ints(c->ns, c->npts) : 0;
+    const i64 rbd_wp = c->rbg_set ? (i64)c->ngx * c->ngy * c->ns * c->ns : c->rbd_set ? tpp_lut_doubles(c->ns, c->npts) : 0;
+    const i64 rbd_iwp = c->rbg_set ? (i64)c->ngx * c->ngy * c->ns : c->rbd_set ? tpp_pt_ints(c->ns, c->npts) : 0;
     if (alloc_solver(c, h.neq, h.maxl, h.kmp, 0, h.has_id, 0, h.has_tol, h.lenwp - rbd_wp, h.leniwp - rbd_iwp) != 0) return DKB_E_CUDA;
     if (c->lenwp != h.lenwp || c->leniwp != h.leniwp) return dkb_fail(DKB_E_ARG, "dkb_state_import: preconditioner storage differs");
     c->neq_g = h.neq_g; c->s_lid = h.s_lid; c->s_lenid = h.s_lenid; c->s_nonneg = h.s_nonneg; c->s_ncphi = h.s_ncphi;

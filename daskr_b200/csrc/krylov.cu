@@ -85,7 +85,7 @@ bool builtin_fused(dkb_res_t res, dkb_psol_t psol, const int *ipar)
     DkbCtx *c = g_ctx;
     if (!c->opt_fused || !c->rbd_set) return false;
     if (c->problem == DKB_PROB_WEB && res == dkb_web_res && psol == dkb_web_psol)
-        return ipar != nullptr && ipar[0] == 1 && ipar[1] == 0;
+        return ipar != nullptr && (ipar[0] == 1 || ipar[0] == 3) && ipar[1] == 0;   // jpre = 1 or 3, no block grouping
     if (c->problem == DKB_PROB_HEAT && res == dkb_heat_res && psol == dkb_heat_psol) return true;
     return false;
 }
@@ -100,6 +100,7 @@ struct GmresArgs {
     double *rpar;
     int *ipar;
     bool fused;
+    int jpre;   // food web: ipar(1)
 };
 
 // datv, src/daskr_new.f90:3429-3520: vnext = D^-1 P^-1 (dF/dy) D v
@@ -111,9 +112,9 @@ static void k_datv(const GmresArgs &A, const double *v, double *vnext, int *ires
     *ierr = 0;
     if (A.fused) {
         if (c->nranks > 1) halo_exchange(const_cast<double *>(v));
-        if (c->problem == DKB_PROB_WEB)
-            web_datv_fused(v, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, c->iwp, vnext);
-        else
+        if (c->problem == DKB_PROB_WEB) {
+            if (web_datv_fused(v, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, c->iwp, vnext, A.jpre) != 0) *ierr = -1;
+        } else
             heat_datv_fused(v, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, vnext);
         *nres += 1;
         *npsol += 1;
@@ -198,10 +199,16 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
     if (nrsts == 0) {
         ProfScope ps(PROF_PSOL0);
         if (A.fused) {
-            if (c->ns == 1)
+            if (c->ns == 1) {
                 lu_psol_scaled(c->wp, c->iwp, 1, c->npts, A.x, A.wt, A.rsqrtn, v[0], S_RNORM);
-            else
+            } else if (A.jpre == 3) {   // A_S (Gauss-Seidel, in place on a copy of the rhs) then A_R
+                double *r = v[maxl];
+                v_copy(neq, A.x, r);
+                if (web_gauss_seidel(1.0 / A.cj, r, c->wk) != 0) ierr = -1;
+                tpp_psol(c->wp, c->iwp, c->ns, c->npts, r, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
+            } else {
                 tpp_psol(c->wp, c->iwp, c->ns, c->npts, A.x, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
+            }
         } else {
             double *r = v[maxl];   // r is v(:,maxl+1), dslvk:3114
             v_copy(neq, A.x, r);
@@ -324,6 +331,7 @@ void k_dslvk(i64 neq, const double *y, double t, const double *ydot, const doubl
     A.rpar = rpar;
     A.ipar = ipar;
     A.fused = builtin_fused(res, psol, ipar);
+    A.jpre = (A.fused && c->problem == DKB_PROB_WEB) ? ipar[0] : 1;
 
     // The reference scales ewt by 1/sqrt(N) in place (:3120) and back on exit (:3163).  Here the
     // weights stay untouched: fused kernels form wght = rsqrtn*wt on the fly (same product,

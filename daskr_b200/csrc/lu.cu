@@ -106,6 +106,58 @@ __global__ void __launch_bounds__(128) dgesl_tpp_ref_kernel(const double *__rest
     }
 }
 
+// psol_rbgpre, src/daskr_rbgpre.f90:278-304: every mesh point is solved with the factors of its group.  Thread per
+// point; the ngrp blocks (25 x 3.2 KB in the example) stay in L1/L2 and the 32 points of a warp mostly share one.
+template <int NS>
+__global__ void __launch_bounds__(128) rbg_psol_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
+                                                       const int *__restrict__ jigx, const int *__restrict__ jigy,
+                                                       int mx, int jy0, int ngx, i64 npts, double *__restrict__ bv)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 p = (i64)blockIdx.x * blockDim.x + threadIdx.x; p < npts; p += stride) {
+        const int jyl = (int)(p / mx), jx = (int)(p - (i64)jyl * mx);
+        const int ig = (__ldg(jigy + jy0 + jyl) - 1) * ngx + (__ldg(jigx + jx) - 1);
+        const double *a = bd + (i64)ig * (NS * NS);
+        const int *pv = ipbd + (i64)ig * NS;
+        double b[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) b[i] = bv[p * NS + i];
+#pragma unroll
+        for (int k = 0; k < NS - 1; ++k) {
+            const int l = __ldg(pv + k) - 1;
+            const double bk = b[k];
+            double t = bk;
+#pragma unroll
+            for (int i = k + 1; i < NS; ++i)
+                if (i == l) {
+                    t = b[i];
+                    b[i] = bk;
+                }
+            b[k] = t;
+#pragma unroll
+            for (int i = k + 1; i < NS; ++i) b[i] = b[i] + t * __ldg(a + k * NS + i);
+        }
+#pragma unroll
+        for (int k = NS - 1; k >= 0; --k) {
+            b[k] = b[k] / __ldg(a + k * NS + k);
+            const double t = -b[k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) b[i] = b[i] + t * __ldg(a + k * NS + i);
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) bv[p * NS + i] = b[i];
+    }
+}
+
+__global__ void rbg_add_cj_kernel(double *bd, int ns, int nsd, int ngrp, double cj)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // (group, diagonal index)
+    if (e >= ngrp * nsd) return;
+    const int g = e / nsd, i = e - g * nsd;
+    double *d = bd + (i64)g * ns * ns + (i64)i * (ns + 1);
+    *d = *d + cj;   // jac_rbgpre:259-262
+}
+
 template <int NS>
 __global__ void __launch_bounds__(256) dgesl_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
                                                     i64 nblk, double *b)
@@ -246,6 +298,26 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
         NS_DISPATCH(ns, CALL)
 #undef CALL
     }
+    COUNT_LAUNCH();
+    return 0;
+}
+
+void rbg_add_cj(double *bd, int ns, int nsd, int ngrp, double cj)
+{
+    const int n = ngrp * nsd;
+    if (n <= 0) return;
+    rbg_add_cj_kernel<<<(n + 127) / 128, 128, 0, g_ctx->stream>>>(bd, ns, nsd, ngrp, cj);
+    COUNT_LAUNCH();
+}
+
+int rbg_psol(const double *bd, const int *ipbd, double *b)
+{
+    DkbCtx *c = g_ctx;
+    const i64 npts = c->npts;
+    const int grid = (int)std::min<i64>((npts + 127) / 128, 148 * 16);
+#define CALL(N) rbg_psol_kernel<N><<<grid, 128, 0, c->stream>>>(bd, ipbd, c->d_jigx, c->d_jigy, c->mx, c->jy0, c->ngx, npts, b)
+    NS_DISPATCH(c->ns, CALL)
+#undef CALL
     COUNT_LAUNCH();
     return 0;
 }

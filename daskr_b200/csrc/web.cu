@@ -96,8 +96,9 @@ template <int NS, bool DATV>
 __global__ void __launch_bounds__(RT<NS>::THREADS)
 web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
                    const double *__restrict__ y, const double *__restrict__ ydot, double cj,
-                   double *__restrict__ out)
+                   const double *__restrict__ sub, double *__restrict__ out)
 {
+    // sub != nullptr: out = G - sub (datv's "vtemp - savr", src/daskr_new.f90:3509, folded into the store)
     constexpr int TX = RT<NS>::TX, THREADS = RT<NS>::THREADS;
     constexpr int ZX = TX + 2;
     constexpr int NHALO = (2 * TX + 2 * RT_TY) * NS;
@@ -196,7 +197,9 @@ web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restr
         const double dcyli = ci - Z[pyl * NS + i], dcyui = Z[pyu * NS + i] - ci;
         const double dcxli = ci - Z[(pt + dxl) * NS + i], dcxui = Z[(pt + dxu) * NS + i] - ci;
         const double f = cyi * (dcyui - dcyli) + cxi * (dcxui - dcxli) + R;
-        out[(i64)gy * mxns + (i64)gx * NS + i] = (i >= w.np) ? -f : (ydt[ry] - f);
+        const i64 o = (i64)gy * mxns + (i64)gx * NS + i;
+        const double g = (i >= w.np) ? -f : (ydt[ry] - f);
+        out[o] = sub ? g - sub[o] : g;
     }
 }
 
@@ -304,7 +307,7 @@ static int grp_grid(i64 npts, int G, int block, int per_sm)
 
 template <int NS, bool DATV>
 static void restile_launch(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
-                           const double *ydot, double cj, double *out)
+                           const double *ydot, double cj, const double *sub, double *out)
 {
     static bool attr_set = false;
     constexpr int TX = RT<NS>::TX;
@@ -314,14 +317,14 @@ static void restile_launch(const WebDev &w, const double *v, const double *wt, d
         attr_set = true;
     }
     const int tiles = ((w.mx + TX - 1) / TX) * ((w.my + RT_TY - 1) / RT_TY);
-    web_restile_kernel<NS, DATV><<<tiles, RT<NS>::THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, out);
+    web_restile_kernel<NS, DATV><<<tiles, RT<NS>::THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, sub, out);
     COUNT_LAUNCH();
 }
 
 void web_res_launch(const double *c, const double *cdot, double *delta)
 {
     WebDev w = make_webdev();
-#define CALL(N) restile_launch<N, false>(w, nullptr, nullptr, 1.0, c, cdot, 0.0, delta)
+#define CALL(N) restile_launch<N, false>(w, nullptr, nullptr, 1.0, c, cdot, 0.0, nullptr, delta)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
 }
@@ -339,22 +342,96 @@ void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, 
     COUNT_LAUNCH();
 }
 
+// ---------------------------------------------------------------- block grouping (jbg = 1)
+// jac_rbgpre, src/daskr_rbgpre.f90:195-254: one FD block per GROUP, evaluated at the group's representative point.
+// Same arithmetic as web_jac_kernel; the block is written unfactored in the reference layout (group g at g*ns^2,
+// column-major) -- zeros if the representative point lives on another rank -- so that the ranks can sum their
+// parts before cj*I_d is added and the blocks are factored.
+template <int NS>
+__global__ void __launch_bounds__(128) web_jac_groups_kernel(WebDev w, const i64 *__restrict__ rep, int ngrp,
+                                                             const double *__restrict__ c,
+                                                             const double *__restrict__ rewt, double *__restrict__ bd)
+{
+    constexpr int G = GroupOf<NS>::G;
+    const unsigned mask = group_mask<G>();
+    const int li = threadIdx.x % G;
+    const int lic = li < NS ? li : 0;
+    const int gpb = blockDim.x / G;
+    double arow[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) arow[j] = w.acoef[j * NS + lic];
+    const double bco = w.bcoef[lic];
+    const int nloop = (ngrp + gridDim.x * gpb - 1) / (gridDim.x * gpb);
+    for (int it = 0; it < nloop; ++it) {
+        int g = blockIdx.x * gpb + threadIdx.x / G + it * gridDim.x * gpb;
+        const bool live = g < ngrp;
+        if (!live) g = ngrp - 1;
+        const i64 pr = rep[g];
+        const bool own = pr >= 0;
+        const i64 p = own ? pr : 0;
+        const i64 idx = p * NS + lic;
+        const double ci = __ldg(c + idx);
+        const double rw = __ldg(rewt + idx);
+        const int jyl = (int)(p / w.mx);
+        const int jx = (int)(p - (i64)jyl * w.mx);
+        const double fac = web_fac_xy(w, jx, w.jy0 + jyl);
+        double cb[NS], del[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            cb[j] = __shfl_sync(mask, ci, j, G);
+            const double rj = __shfl_sync(mask, rw, j, G);
+            del[j] = fmax(w.srur * fabs(cb[j]), 1e-2 / rj);   // jac_rbgpre:233
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) r = r + cb[j] * arow[j];
+        const double r0 = ci * (bco * fac + r);
+#pragma unroll
+        for (int js = 0; js < NS; ++js) {
+            const double up = cb[js] + del[js];
+            const double fd = -1.0 / del[js];
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; ++j) s = s + ((j == js) ? up : cb[j]) * arow[j];
+            const double cown = (li == js) ? up : ci;
+            const double r1 = cown * (bco * fac + s);
+            if (live && li < NS) bd[(i64)g * (NS * NS) + js * NS + li] = own ? (r1 - r0) * fd : 0.0;
+        }
+    }
+}
+
+void web_jac_groups_launch(const double *c, const double *rewt, double *bd)
+{
+    DkbCtx *x = g_ctx;
+    WebDev w = make_webdev();
+    const int ngrp = x->ngx * x->ngy;
+#define CALL(N) web_jac_groups_kernel<N><<<(ngrp * GroupOf<N>::G + 127) / 128, 128, 0, x->stream>>>(w, x->d_rep, ngrp, c, rewt, bd)
+    WEB_DISPATCH(w.ns, CALL)
+#undef CALL
+    COUNT_LAUNCH();
+}
+
 // datv (src/daskr_new.f90:3429-3520) for the built-in problem: vtemp = G(z, ydottemp) into the
 // ydottemp slot (free here: ydottemp is never materialised), then the block solve with the
 // "- savr" and "* wght" statements folded into its load / store phases.
-void web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
-                    const double *savr, double cj, const double *bd, const int *ipbd, double *vnext)
+// jpre = 3 (example_web.f90:346-391, the shipped setting): the Gauss-Seidel factor runs between the two, on
+// vtemp - savr (the subtraction folded into the residual kernel's store).
+int web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+                   const double *savr, double cj, const double *bd, const int *ipbd, double *vnext, int jpre)
 {
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
     // one kernel when the mesh allows it (warp = 32 consecutive points of a row = one LU tile)
-    if (x->opt_fused >= 2 && web_datv_single(w, v, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)) return;
+    if (jpre == 1 && x->opt_fused >= 2 && web_datv_single(w, v, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)) return 0;
     double *vtemp = x->z;
+    const double *sub = (jpre == 1) ? nullptr : savr;
     {
         ProfScope ps(PROF_RESDATV);
-#define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, vtemp)
+#define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, sub, vtemp)
         WEB_DISPATCH(w.ns, CALL)
 #undef CALL
     }
-    tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, savr, wt, wscale, vnext, -1);
+    if (jpre != 1 && web_gauss_seidel(1.0 / cj, vtemp, x->wk) != 0) return -1;
+    tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1);
+    return 0;
 }

@@ -99,6 +99,12 @@ void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *ns
                       const int *lid, int *iwork);
 int dkb_slab(int *jy0, int *myloc);
 
+/* setup_rbgpre (DGSET2), src/daskr_rbgpre.f90:107-158: the block-grouped variant, nxg x nyg groups of mesh points
+ * sharing one block (the block of the group's representative point).  Same arguments as the reference; replaces
+ * dkb_setup_rbdpre for runs with jbg = ipar(2) = 1 of the food-web routines (example_web.f90:873-877). */
+void dkb_setup_rbgpre(const int *mx, const int *my, const int *ns, const int *nsd, const int *nxg, const int *nyg,
+                      const int *lid, int *iwork);
+
 /* ---- built-in device problems (the user routines of the two examples) ---- */
 /* food web, example/example_web.f90:5-60 (setpar) with np, mx, my at run time */
 int dkb_web_setpar(int np, int mx, int my);

@@ -1609,9 +1609,27 @@ static void steplog_push(const int *iwork)
  * does: first call computes consistent initial values (info(11)=1,
  * info(14)=1 -> idid=4), then info(11)=0 and integration restarts from the
  * corrected values.  nrt=0 (rootfinding does not alter the step sequence). */
+static int run_web_impl(int nxg, int nyg, int np, int mx, int my, int jpre, double rtol_, double atol_,
+                        int nout, const double *touts, double *yout, int *counters,
+                        double *rhead, long max_steps, double *tfinal);
+
 int o_run_web(int np, int mx, int my, int jpre, double rtol_, double atol_,
               int nout, const double *touts, double *yout, int *counters,
               double *rhead, long max_steps, double *tfinal)
+{
+    return run_web_impl(0, 0, np, mx, my, jpre, rtol_, atol_, nout, touts, yout, counters, rhead, max_steps, tfinal);
+}
+
+int o_run_web_bg(int nxg, int nyg, int np, int mx, int my, int jpre, double rtol_, double atol_,
+                 int nout, const double *touts, double *yout, int *counters,
+                 double *rhead, long max_steps, double *tfinal)
+{
+    return run_web_impl(nxg, nyg, np, mx, my, jpre, rtol_, atol_, nout, touts, yout, counters, rhead, max_steps, tfinal);
+}
+
+static int run_web_impl(int nxg, int nyg, int np, int mx, int my, int jpre, double rtol_, double atol_,
+                        int nout, const double *touts, double *yout, int *counters,
+                        double *rhead, long max_steps, double *tfinal)
 {
     o_web_setpar(np, mx, my);
     const int ns = 2 * np;
@@ -1624,9 +1642,11 @@ int o_run_web(int np, int mx, int my, int jpre, double rtol_, double atol_,
     info[13] = 1; /* info(14) */
     info[14] = 1; /* info(15) */
     info[15] = 1; /* info(16) */
-    int ipar[2] = {jpre, 0};
+    const int jbg = (nxg > 0) ? 1 : 0;
+    int ipar[2] = {jpre, jbg};
     std::vector<int> iwork(40 + 2 * neq + 16, 0);
-    o_setup_rbdpre(mx, my, ns, np, 40, iwork.data());
+    if (jbg == 0) o_setup_rbdpre(mx, my, ns, np, 40, iwork.data());
+    else o_setup_rbgpre(mx, my, ns, np, nxg, nyg, 40, iwork.data());
     long lenwp = iwork[26];
     long lrw = 104 + 19 * neq + lenwp + 64;
     long liw = (long)iwork.size();

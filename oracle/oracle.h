@@ -95,6 +95,11 @@ void o_dslvk(long neq, const double *y, double t, const double *ydot,
 
 /* ---- reaction-based block-diagonal preconditioner, src/daskr_rbdpre.f90 ---- */
 void o_setup_rbdpre(int mx, int my, int ns, int nsd, int lid, int *iwork);
+/* src/daskr_rbgpre.f90:107-304 (block grouping) */
+void o_setup_rbgpre(int mx, int my, int ns, int nsd, int nxg, int nyg, int lid, int *iwork);
+void o_jac_rbgpre(double t, double *u, const double *r0, o_rblock_t rblock, double *r1,
+                  const double *rewt, double cj, double *bd, int *ipbd, int *ierr);
+void o_psol_rbgpre(double *b, const double *bd, const int *ipbd);
 void o_jac_rbdpre(double t, double *u, const double *r0, o_rblock_t rblock,
                   double *r1, const double *rewt, double cj, double *bd,
                   int *ipbd, int *ierr);
@@ -151,6 +156,10 @@ void o_heat_psol(const int *neq, const double *t, const double *u,
  * counters[nout][40]; rwork(1:60)-header in rhead[nout][60].
  * max_steps > 0 stops after that many BDF steps (benchmark budget).  Returns idid. */
 int o_run_web(int np, int mx, int my, int jpre, double rtol, double atol,
+              int nout, const double *touts, double *yout, int *counters,
+              double *rhead, long max_steps, double *tfinal);
+/* same with block grouping (jbg = 1, nxg x nyg groups; example_web.f90:873-877 uses 5 x 5) */
+int o_run_web_bg(int nxg, int nyg, int np, int mx, int my, int jpre, double rtol, double atol,
               int nout, const double *touts, double *yout, int *counters,
               double *rhead, long max_steps, double *tfinal);
 void o_set_steplog(double *buf, long cap);   /* (wall s, NLI, NST) per step, max_steps mode */

@@ -104,6 +104,117 @@ void o_psol_rbdpre(double *b, const double *bd, const int *ipbd)
 }
 
 /* ------------------------------------------------------------------ */
+/* block-grouped variant: src/daskr_rbgpre.f90                          */
+/* ------------------------------------------------------------------ */
+static int g_ngx, g_ngy, g_ngrp;
+static std::vector<int> g_jgx, g_jgy, g_jigx, g_jigy, g_jxr, g_jyr; /* 1-based, element 0 unused */
+
+/* src/daskr_rbgpre.f90:160-193 (set_grouping) */
+static void set_grouping(int m, int ng, std::vector<int> &jg, std::vector<int> &jig, std::vector<int> &jr)
+{
+    int mper = m / ng;
+    for (int ig = 1; ig <= ng; ++ig) jg[ig] = 1 + (ig - 1) * mper;
+    jg[ng + 1] = m + 1;
+    int ngm1 = ng - 1;
+    int len1 = ngm1 * mper;
+    for (int j = 1; j <= len1; ++j) jig[j] = 1 + (j - 1) / mper;
+    len1 = len1 + 1;
+    for (int j = len1; j <= m; ++j) jig[j] = ng;
+    for (int ig = 1; ig <= ngm1; ++ig) jr[ig] = (int)(0.5 + ((double)ig - 0.5) * mper);
+    jr[ng] = (int)(0.5 * (1 + ngm1 * mper + m));
+}
+
+/* src/daskr_rbgpre.f90:107-158 */
+void o_setup_rbgpre(int mx, int my, int ns, int nsd, int nxg, int nyg, int lid, int *iwork)
+{
+    int *IW = iwork - 1;
+    srur = std::sqrt(2.220446049250313e-16);
+    mp = ns;
+    mpd = nsd;
+    mpsq = ns * ns;
+    meshx = mx;
+    meshy = my;
+    mxmp = meshx * mp;
+    g_ngx = nxg;
+    g_ngy = nyg;
+    g_ngrp = nxg * nyg;
+    int maxm = std::max(meshx, meshy);
+    g_jgx.assign(maxm + 2, 0); g_jgy.assign(maxm + 2, 0);
+    g_jigx.assign(maxm + 1, 0); g_jigy.assign(maxm + 1, 0);
+    g_jxr.assign(maxm + 1, 0); g_jyr.assign(maxm + 1, 0);
+    set_grouping(meshx, g_ngx, g_jgx, g_jigx, g_jxr);
+    set_grouping(meshy, g_ngy, g_jgy, g_jigy, g_jyr);
+    IW[27] = mpsq * g_ngrp;
+    IW[28] = mp * g_ngrp;
+    if (lid == 0) return;
+    long i0 = lid;
+    for (int jy = 1; jy <= my; ++jy)
+        for (int jx = 1; jx <= mx; ++jx) {
+            for (int i = 1; i <= mpd; ++i) IW[i0 + i] = 1;
+            for (int i = mpd + 1; i <= mp; ++i) IW[i0 + i] = -1;
+            i0 = i0 + mp;
+        }
+}
+
+/* src/daskr_rbgpre.f90:195-276: one block per group, evaluated at the group's representative point */
+void o_jac_rbgpre(double t, double *u, const double *r0, o_rblock_t rblock, double *r1,
+                  const double *rewt, double cj, double *bd, int *ipbd, int *ierr)
+{
+    const double dfac = 1e-2;
+    long ibd = 0;
+    for (int igy = 1; igy <= g_ngy; ++igy) {
+        int jy = g_jyr[igy];
+        long j00 = (long)(jy - 1) * mxmp;
+        for (int igx = 1; igx <= g_ngx; ++igx) {
+            int jx = g_jxr[igx];
+            long j0 = j00 + (long)(jx - 1) * mp;
+            for (int js = 1; js <= mp; ++js) {
+                long j = j0 + js;
+                double uj = u[j - 1];
+                double del = std::max(srur * std::fabs(uj), dfac / rewt[j - 1]);
+                u[j - 1] = u[j - 1] + del;
+                double fac = -1.0 / del;
+                rblock(&t, &jx, &jy, &u[j0], r1);
+                for (int i = 1; i <= mp; ++i) bd[ibd + i - 1] = (r1[i - 1] - r0[j0 + i - 1]) * fac;
+                u[j - 1] = uj;
+                ibd = ibd + mp;
+            }
+        }
+    }
+    ibd = 1;
+    long iip = 1;
+    for (int ig = 1; ig <= g_ngrp; ++ig) {
+        long idiag = ibd;
+        for (int i = 1; i <= mp; ++i) {
+            if (i <= mpd) bd[idiag - 1] = bd[idiag - 1] + cj;
+            idiag = idiag + (mp + 1);
+        }
+        o_dgefa(&bd[ibd - 1], mp, mp, &ipbd[iip - 1], ierr);
+        if (*ierr != 0) break;
+        ibd = ibd + mpsq;
+        iip = iip + mp;
+    }
+}
+
+/* src/daskr_rbgpre.f90:278-304: every mesh point is solved with its group's factors */
+void o_psol_rbgpre(double *b, const double *bd, const int *ipbd)
+{
+    long ib = 1;
+    for (int jy = 1; jy <= meshy; ++jy) {
+        int igy = g_jigy[jy];
+        int ig0 = (igy - 1) * g_ngx;
+        for (int jx = 1; jx <= meshx; ++jx) {
+            int igx = g_jigx[jx];
+            int igm1 = igx - 1 + ig0;
+            long ibd = 1 + (long)igm1 * mpsq;
+            long iip = 1 + (long)igm1 * mp;
+            o_dgesl(&bd[ibd - 1], mp, mp, &ipbd[iip - 1], &b[ib - 1], 0);
+            ib = ib + mp;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* food web: module web_par, example/example_web.f90:5-60              */
 /* ------------------------------------------------------------------ */
 static int w_np, w_ns, w_mx, w_my, w_mxns;
@@ -264,8 +375,10 @@ void o_web_jac(o_res_t res, int *ires, const int *neq, const double *t, double *
                const double *h, const double *cj, double *rwp, int *iwp,
                int *ierr, double *rpar, int *ipar)
 {
-    (void)res; (void)ires; (void)neq; (void)cdot; (void)savr; (void)h; (void)ipar;
-    o_jac_rbdpre(*t, c, rpar, o_web_rates, wk, rewt, *cj, rwp, iwp, ierr);
+    (void)res; (void)ires; (void)neq; (void)cdot; (void)savr; (void)h;
+    int jbg = ipar[1]; /* example_web.f90:337-342 */
+    if (jbg == 0) o_jac_rbdpre(*t, c, rpar, o_web_rates, wk, rewt, *cj, rwp, iwp, ierr);
+    else o_jac_rbgpre(*t, c, rpar, o_web_rates, wk, rewt, *cj, rwp, iwp, ierr);
 }
 
 /* example/example_web.f90:393-575 -- itmax=5 lexicographic Gauss-Seidel sweeps
@@ -354,7 +467,7 @@ void o_web_gauss_seidel(long n, double hl0, double *z0, double *x0)
     }
 }
 
-/* example/example_web.f90:346-391; jbg = ipar(2) must be 0 */
+/* example/example_web.f90:346-391 */
 void o_web_psol(const int *neq, const double *t, const double *c, const double *cdot,
                 const double *savr, double *wk, const double *cj, const double *wght,
                 double *rwp, int *iwp, double *b, const double *epslin, int *ierr,
@@ -365,7 +478,10 @@ void o_web_psol(const int *neq, const double *t, const double *c, const double *
     *ierr = 0;
     double hl0 = 1.0 / (*cj);
     if (jpre == 2 || jpre == 3) o_web_gauss_seidel(*neq, hl0, b, wk);
-    if (jpre != 2) o_psol_rbdpre(b, rwp, iwp);
+    if (jpre != 2) {
+        if (ipar[1] == 0) o_psol_rbdpre(b, rwp, iwp);
+        else o_psol_rbgpre(b, rwp, iwp); /* jbg = 1, example_web.f90:385-386 */
+    }
     if (jpre == 4) o_web_gauss_seidel(*neq, hl0, b, wk);
 }
 

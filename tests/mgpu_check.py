@@ -29,12 +29,13 @@ def main():
     ok = True
     # jpre = 3 (last column): the spatial Gauss-Seidel factor is block Jacobi over the slabs on several GPUs, so that
     # case agrees with the full-mesh CPU run to the integration tolerance only (counters may differ by a few)
-    cases = [("web", 1, 24, 26, True, 1), ("web", 1, 24, 26, False, 1), ("web", 10, 16, 18, True, 1), ("heat", 0, 30, 0, True, 1),
-             ("web", 1, 40, 44, True, 3), ("web", 10, 36, 40, True, 3)]
-    for kind, np_, mx, my, fused, jpre in cases:
+    cases = [("web", 1, 24, 26, True, 1, 0), ("web", 1, 24, 26, False, 1, 0), ("web", 10, 16, 18, True, 1, 0),
+             ("heat", 0, 30, 0, True, 1, 0), ("web", 1, 40, 44, True, 3, 0), ("web", 10, 36, 40, True, 3, 0),
+             ("web", 1, 40, 44, True, 3, 5), ("web", 2, 30, 33, True, 1, 4)]   # last column: block grouping, ng x ng groups
+    for kind, np_, mx, my, fused, jpre, ng in cases:
         if kind == "web":
             touts = [1e-8, 1e-6, 1e-4, 1e-3, 1e-2]
-            g = dk.solve_web(np_, mx, my, touts, fused=fused, jpre=jpre)
+            g = dk.solve_web(np_, mx, my, touts, fused=fused, jpre=jpre, nxg=ng, nyg=ng)
             rtol, atol = 1e-5, 1e-5
         else:
             touts = [0.01 * 2 ** n for n in range(6)]
@@ -47,7 +48,7 @@ def main():
             from tests import oracle_py
 
             orc = oracle_py.load()
-            o = orc.run_web(np_, mx, my, touts, jpre=jpre) if kind == "web" else orc.run_heat(mx, touts)
+            o = orc.run_web(np_, mx, my, touts, jpre=jpre, nxg=ng, nyg=ng) if kind == "web" else orc.run_heat(mx, touts)
             full = np.concatenate(gathered, axis=1)
             assert full.shape == o["y"].shape, (full.shape, o["y"].shape)
             w = 1.0 / (rtol * np.abs(o["y"]) + atol)
@@ -55,8 +56,8 @@ def main():
             cg, co = g["counters"][-1], o["counters"][-1]
             good = g["idid"] == o["idid"] == 3 and err.max() <= 10.0
             ok = ok and good
-            print("%s np=%d %dx%d fused=%s jpre=%d world=%d: max wrms(diff)/tol=%.3e  NST %d/%d NNI %d/%d NLI %d/%d NJE %d/%d -> %s"
-                  % (kind, np_, mx, my, fused, jpre, world, err.max(), cg[10], co[10], cg[18], co[18], cg[19], co[19], cg[12], co[12],
+            print("%s np=%d %dx%d fused=%s jpre=%d groups=%d world=%d: max wrms(diff)/tol=%.3e  NST %d/%d NNI %d/%d NLI %d/%d NJE %d/%d -> %s"
+                  % (kind, np_, mx, my, fused, jpre, ng, world, err.max(), cg[10], co[10], cg[18], co[18], cg[19], co[19], cg[12], co[12],
                      "OK" if good else "FAIL"), flush=True)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)

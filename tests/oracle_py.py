@@ -53,6 +53,8 @@ def load():
     L.o_run_web.restype = C.c_int
     L.o_run_web.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+    L.o_run_web_bg.restype = C.c_int
+    L.o_run_web_bg.argtypes = [C.c_int, C.c_int] + list(L.o_run_web.argtypes)
     L.o_run_heat.restype = C.c_int
     L.o_run_heat.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_long, C.c_void_p]
@@ -136,7 +138,8 @@ class Oracle:
         return x
 
     # ---- whole runs ----
-    def run_web(self, np_, mx, my, touts, jpre=1, rtol=1e-5, atol=1e-5, max_steps=0):
+    def run_web(self, np_, mx, my, touts, jpre=1, rtol=1e-5, atol=1e-5, max_steps=0, nxg=0, nyg=0):
+        """nxg, nyg > 0: block grouping (jbg = 1, src/daskr_rbgpre.f90)."""
         neq = 2 * np_ * mx * my
         nout = len(touts)
         touts = np.asarray(touts, dtype=np.float64)
@@ -144,8 +147,12 @@ class Oracle:
         cnt = np.zeros((nout, 40), dtype=np.int32)
         rh = np.zeros((nout, 60))
         tf = C.c_double(0)
-        idid = self.L.o_run_web(np_, mx, my, jpre, rtol, atol, nout, _p(touts), _p(y), _p(cnt), _p(rh), max_steps,
-                                C.byref(tf))
+        if nxg > 0:
+            idid = self.L.o_run_web_bg(nxg, nyg, np_, mx, my, jpre, rtol, atol, nout, _p(touts), _p(y), _p(cnt), _p(rh),
+                                       max_steps, C.byref(tf))
+        else:
+            idid = self.L.o_run_web(np_, mx, my, jpre, rtol, atol, nout, _p(touts), _p(y), _p(cnt), _p(rh), max_steps,
+                                    C.byref(tf))
         return dict(y=y, counters=cnt, rhead=rh, idid=idid, t=tf.value)
 
     def run_heat(self, m, touts, rtol=0.0, atol=1e-5, max_steps=0):
