@@ -247,6 +247,9 @@ int dkb_finalize(void)
     cudaFree(c->d_sx);
     cudaFree(c->gs_z);
     cudaFree(c->gs_x);
+    cudaFree(c->gs_ticket);
+    cudaFree(c->gs_done);
+    cudaFree(c->gs_first);
     cudaFree(c->d_jigx);
     cudaFree(c->d_jigy);
     cudaFree(c->d_rep);

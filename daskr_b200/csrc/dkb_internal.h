@@ -97,6 +97,10 @@ struct DkbCtx {
     int rbg_set = 0, ngx = 0, ngy = 0;
     int *d_jigx = nullptr, *d_jigy = nullptr;
     i64 *d_rep = nullptr;
+    unsigned *gs_ticket = nullptr, *gs_done = nullptr;   // gs.cu: persistent-sweep scheduler state
+    int *gs_first = nullptr;
+    unsigned gs_epoch = 0;
+    int gs_ntx = 0, gs_nty = 0, gs_nt = 0, gs_total = 0;
     double *gs_z = nullptr, *gs_x = nullptr;   // gs.cu: overlapped-slab work vectors (several ranks only)
     i64 gs_cap = 0;
     double *d_scal = nullptr;    // DKB_NSLOT doubles

@@ -73,8 +73,8 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
         const bool has_hb = jy0 > 0 && mine;
 #pragma unroll
         for (int k = 0; k < 2; ++k)                               // this iteration's values of the left tile
-            if (jx0 > 0 && q + 32 * k < hgt) hl[k] = x[(i64)(jy0 + q + 32 * k) * mxns + (i64)(jx0 - 1) * NS + g0 + i];
-        if (has_hb) hb = x[col0 - mxns];                          // ... and of the tile below
+            if (jx0 > 0 && q + 32 * k < hgt) hl[k] = __ldcg(&x[(i64)(jy0 + q + 32 * k) * mxns + (i64)(jx0 - 1) * NS + g0 + i]);
+        if (has_hb) hb = __ldcg(&x[col0 - mxns]);                         // ... and of the tile below
 
         const double b1 = a.beta1[g0 + ic], g1 = a.gamma1[g0 + ic], dinv = a.dinv[g0 + ic];
         const double betU = (jx == 1) ? 2 * b1 : b1;              // (D-inverse)*U*x (:486-530)
@@ -86,8 +86,8 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             double v1[UA], v2[UA];
 #pragma unroll
             for (int u = 0; u < UA; ++u) {
-                v1[u] = src[u * mxns];
-                if (!IT1) v2[u] = src[u * mxns + ((edge && r0 + u == rtop) ? 0 : upo)];   // no row above the last one
+                v1[u] = __ldcg(&src[u * mxns]);
+                if (!IT1) v2[u] = __ldcg(&src[u * mxns + ((edge && r0 + u == rtop) ? 0 : upo)]);   // no row above the last one
             }
 #pragma unroll
             for (int u = 0; u < UA; ++u) {
@@ -104,13 +104,13 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             }
         }
         for (; r0 < hgt; ++r0, src += mxns) {                     // rows of a partial last batch
-            const double v1 = src[0];
+            const double v1 = __ldcg(&src[0]);
             double uu;
             if (IT1) {
                 uu = dinv * v1;
             } else {
                 const bool lasty = r0 == rtop;
-                const double v2 = src[lasty ? 0 : upo];
+                const double v2 = __ldcg(&src[lasty ? 0 : upo]);
                 const double gam = (r0 == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
                 const double t1 = betU * v1, t2 = gam * v2;
                 uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
@@ -127,7 +127,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
     // z of the first UC rows for phase C: in flight while phase B runs
     double zin0[UC];
 #pragma unroll
-    for (int u = 0; u < UC; ++u) zin0[u] = IT1 ? 0.0 : z[col0 + min(u, hgt - 1) * mxns];
+    for (int u = 0; u < UC; ++u) zin0[u] = IT1 ? 0.0 : __ldcg(&z[col0 + min(u, hgt - 1) * mxns]);
     __syncthreads();
     GS_CLK(2);
 
@@ -163,6 +163,8 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
                 __syncwarp();
             }
         } else {
+            // (a branch-free body -- idle lanes computing on valid addresses and dropping the result -- was slower:
+            // 1.85 vs 1.56 ms at 1024x1024x20)
 #pragma unroll 4
             for (int s = 0; s < nsteps; ++s) {
                 if ((unsigned)(s - lane) < nrow) {
@@ -191,7 +193,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             double zin[UC];
             const bool more = !IT1 && r0 + UC < hgt;            // prefetch the next batch of z before storing this one
 #pragma unroll
-            for (int u = 0; u < UC; ++u) zin[u] = more ? zo[min(UC + u, hgt - 1 - r0) * mxns] : 0.0;
+            for (int u = 0; u < UC; ++u) zin[u] = more ? __ldcg(&zo[min(UC + u, hgt - 1 - r0) * mxns]) : 0.0;
             if (mine) {
 #pragma unroll
                 for (int u = 0; u < UC; ++u) {
@@ -242,6 +244,84 @@ __global__ void __launch_bounds__(32 * SPC) gs_step_kernel(const __grid_constant
     if (iter == 0) return;
     if (iter == 1) gs_tile<NS, SPC, true>(a, I, J, g0, z, x, sm, t);
     else gs_tile<NS, SPC, false>(a, I, J, g0, z, x, sm, t);
+}
+
+// ---- persistent variant: one launch per application ----
+// The tiles are numbered in the order of the launch schedule above (time step, then sweep, then column), and the
+// CTAs of ONE launch take them from an atomic ticket counter.  Before working on a tile a CTA waits for the four
+// tiles it depends on -- (I-1,J) and (I,J-1) of its own sweep, (I+1,J) and (I,J+1) of the previous sweep -- to be
+// flagged done.  All of them have smaller numbers, so they have been taken by CTAs that are running (a CTA only takes
+// a ticket when it is resident): the tile with the smallest unfinished number never waits, and the sweep cannot
+// deadlock whatever the number of resident CTAs.  What this buys over one launch per time step: no grid-wide
+// barrier per step, no partial waves -- an SM starts its next tile as soon as that tile's own inputs exist.
+// Loads of x and z go to L2 (__ldcg): L1 is not coherent between SMs inside a launch.
+struct GsSched {
+    unsigned *ticket;          // next tile number
+    unsigned *done;            // [GS_ITMAX][nty][ntx]: == epoch when the tile of this application is finished
+    const int *first;          // first[t] = number of tiles before time step t, first[nt] = total
+    unsigned epoch;
+    int nt, total;
+};
+
+__device__ __forceinline__ void gs_wait(const unsigned *flag, unsigned epoch)
+{
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) break;
+        __nanosleep(64);
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_constant__ GsArgs a, const GsSched s,
+                                                               double *__restrict__ z, double *__restrict__ x)
+{
+    extern __shared__ double sm[];
+    __shared__ int cur[4];     // iter, I, J, time step (iter = 0: no tiles left)
+    int t = 0;                 // thread 0's cursor into first[]: ticket numbers only grow
+    for (;;) {
+        if (threadIdx.x == 0) {
+            const unsigned n = atomicAdd(s.ticket, 1u);
+            int iter = 0, I = 0, J = 0;
+            if (n < (unsigned)s.total) {
+                while ((int)n >= s.first[t + 1]) ++t;
+                int b = (int)n - s.first[t];
+                for (int k = 0; k < GS_ITMAX; ++k) {
+                    const int d = t - 2 * k;
+                    if (d < 0 || d > a.ntx + a.nty - 2) continue;
+                    const int ilo = max(0, d - (a.nty - 1)), ihi = min(a.ntx - 1, d);
+                    const int cnt = ihi - ilo + 1;
+                    if (b < cnt) {
+                        iter = k + 1;
+                        I = ilo + b;
+                        J = d - I;
+                        break;
+                    }
+                    b -= cnt;
+                }
+                const unsigned *own = s.done + (size_t)(iter - 1) * a.nty * a.ntx;
+                const unsigned *prv = own - (size_t)a.nty * a.ntx;
+                if (I > 0) gs_wait(own + (size_t)J * a.ntx + I - 1, s.epoch);
+                if (J > 0) gs_wait(own + (size_t)(J - 1) * a.ntx + I, s.epoch);
+                if (iter > 1 && I < a.ntx - 1) gs_wait(prv + (size_t)J * a.ntx + I + 1, s.epoch);
+                if (iter > 1 && J < a.nty - 1) gs_wait(prv + (size_t)(J + 1) * a.ntx + I, s.epoch);
+                if (iter > 1) gs_wait(prv + (size_t)J * a.ntx + I, s.epoch);   // the tile's own previous sweep (x, z in place)
+            }
+            cur[0] = iter; cur[1] = I; cur[2] = J; cur[3] = t;
+        }
+        __syncthreads();
+        const int iter = cur[0], I = cur[1], J = cur[2], tt = cur[3];
+        if (iter == 0) return;
+        if (iter == 1) gs_tile<NS, NS, true>(a, I, J, 0, z, x, sm, tt);
+        else gs_tile<NS, NS, false>(a, I, J, 0, z, x, sm, tt);
+        __syncthreads();       // every thread's stores are issued; shared memory is free for the next tile
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned *flag = s.done + ((size_t)(iter - 1) * a.nty + J) * a.ntx + I;
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(s.epoch) : "memory");
+        }
+    }
 }
 
 template <int NS, int SPC>
@@ -337,37 +417,92 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
     const int spc = gs_spc(wp.ns);
     // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
     const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
-    static int ty_knob = -1;   // DKB_GS_TY: tile-height override for tuning runs
-    if (ty_knob < 0) {
-        const char *e = getenv("DKB_GS_TY");
-        ty_knob = e ? std::max(1, std::min(32, atoi(e))) : 0;
-    }
-    int ty = (int)std::min<size_t>(ty_knob ? ty_knob : 32, ((spc == wp.ns ? 200u : 110u) * 1024u) / rowbytes - 1);
+    // Tile height.  32 rows (one CTA per SM) move the fewest halo bytes and win when every SM has work all the time
+    // (17 vs 20 ms at 4096x4096x20); 16 rows (two CTAs per SM, shorter tiles on the critical path) win when the sweep
+    // is dependency-bound (1.56 vs 1.79 ms at 1024x1024x20).  DKB_GS_TY overrides (tests, tuning).
+    const char *ty_env = getenv("DKB_GS_TY");
+    const int ty_want = ty_env ? std::max(1, std::min(32, atoi(ty_env))) : ((i64)a.mx * a.my <= (i64)3 << 20 ? 16 : 32);
+    int ty = (int)std::min<size_t>(ty_want, ((spc == wp.ns ? 200u : 110u) * 1024u) / rowbytes - 1);
     ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
     a.nty = (a.my + ty - 1) / ty;
     const int ndiag = a.ntx + a.nty - 1;
-    for (int t = 0; t < ndiag + 2 * (GS_ITMAX - 1); ++t) {
+    const int nt = ndiag + 2 * (GS_ITMAX - 1);
+    auto tiles_at = [&](int t) {
         int ntile = 0;
         for (int k = 0; k < GS_ITMAX; ++k) {
             const int d = t - 2 * k;
             if (d < 0 || d > ndiag - 1) continue;
             ntile += std::min(a.ntx - 1, d) - std::max(0, d - (a.nty - 1)) + 1;
         }
-        if (ntile == 0) continue;
-#define GS_GO(n, sp) gs_launch<n, sp>(a, ntile, t, z, x, c->stream)
-#define GS_CASE(n) case n: GS_GO(n, n); break;
-#define GS_CASE2(n) case n: if (spc == n) GS_GO(n, n); else GS_GO(n, n / 2); break;
-        switch (wp.ns) {
-            GS_CASE(2) GS_CASE2(4) GS_CASE(6) GS_CASE2(8) GS_CASE(10) GS_CASE2(12) GS_CASE(14) GS_CASE2(16)
-            GS_CASE(18) GS_CASE2(20) GS_CASE(22) GS_CASE2(24) GS_CASE(26) GS_CASE2(28) GS_CASE(30) GS_CASE2(32)
-        }
-#undef GS_GO
-#undef GS_CASE
-#undef GS_CASE2
-        COUNT_LAUNCH();
+        return ntile;
+    };
+    // DKB_GS_PER_STEP=1: one launch per time step (the first version; kept for A/B runs and as a cross-check)
+    const char *ps_env = getenv("DKB_GS_PER_STEP");
+    const int per_step = (ps_env && atoi(ps_env) == 1) ? 1 : 0;
+#define GS_CASES(M) \
+    switch (wp.ns) { \
+        M(2) M(4) M(6) M(8) M(10) M(12) M(14) M(16) M(18) M(20) M(22) M(24) M(26) M(28) M(30) M(32) \
     }
+    if (!per_step) {
+        // ---- one persistent launch: scheduler state (re)built when the tiling changes ----
+        if (c->gs_ntx != a.ntx || c->gs_nty != a.nty || !c->gs_done) {
+            cudaFree(c->gs_ticket);
+            cudaFree(c->gs_done);
+            cudaFree(c->gs_first);
+            c->gs_ticket = c->gs_done = nullptr;
+            c->gs_first = nullptr;
+            std::vector<int> first(nt + 1, 0);
+            for (int t = 0; t < nt; ++t) first[t + 1] = first[t] + tiles_at(t);
+            const size_t nflag = (size_t)GS_ITMAX * a.ntx * a.nty;
+            if (cudaMalloc(&c->gs_ticket, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->gs_done, sizeof(unsigned) * nflag) != cudaSuccess ||
+                cudaMalloc(&c->gs_first, sizeof(int) * (nt + 1)) != cudaSuccess)
+                return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the scheduler state");
+            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * nflag, c->stream);
+            cudaMemcpyAsync(c->gs_first, first.data(), sizeof(int) * (nt + 1), cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);   // `first` is a local
+            c->gs_ntx = a.ntx;
+            c->gs_nty = a.nty;
+            c->gs_nt = nt;
+            c->gs_total = first[nt];
+            c->gs_epoch = 0;
+        }
+        c->gs_epoch += 1;
+        if (c->gs_epoch == 0) {   // wrapped: flags of 2^32 applications ago could alias
+            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * (size_t)GS_ITMAX * a.ntx * a.nty, c->stream);
+            c->gs_epoch = 1;
+        }
+        cudaMemsetAsync(c->gs_ticket, 0, sizeof(unsigned), c->stream);
+        GsSched sch{c->gs_ticket, c->gs_done, c->gs_first, c->gs_epoch, c->gs_nt, c->gs_total};
+        const size_t smem = rowbytes * (a.ty + 1);
+        static int nsm = 0;
+        if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+        // as many CTAs as are resident at once (shared memory decides), fewer if there are fewer tiles
+#define GS_P(n) case n: { \
+            static size_t set = 0; \
+            static int per_sm = 1; \
+            if (smem != set) { \
+                cudaFuncSetAttribute(gs_persistent_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_persistent_kernel<n>, 32 * n, smem); \
+                per_sm = std::max(1, per_sm); \
+                set = smem; \
+            } \
+            gs_persistent_kernel<n><<<std::min(c->gs_total, nsm * per_sm), 32 * n, smem, c->stream>>>(a, sch, z, x); } break;
+        GS_CASES(GS_P)
+#undef GS_P
+        COUNT_LAUNCH();
+    } else {
+        for (int t = 0; t < nt; ++t) {
+            const int ntile = tiles_at(t);
+            if (ntile == 0) continue;
+#define GS_L(n) case n: if (spc == n) gs_launch<n, n>(a, ntile, t, z, x, c->stream); else gs_launch<n, (n % 4 == 0 ? n / 2 : n)>(a, ntile, t, z, x, c->stream); break;
+            GS_CASES(GS_L)
+#undef GS_L
+            COUNT_LAUNCH();
+        }
+    }
+#undef GS_CASES
     dkb_cuda_check("web_gauss_seidel");
     return 0;
 }

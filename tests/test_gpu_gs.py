@@ -46,6 +46,22 @@ def test_gauss_seidel_bit_exact(dk, oracle, np_, mx, my, cj):
     assert np.array_equal(got, z)
 
 
+@pytest.mark.parametrize("env", [{"DKB_GS_TY": "32"}, {"DKB_GS_TY": "7"}, {"DKB_GS_PER_STEP": "1"},
+                                 {"DKB_GS_PER_STEP": "1", "DKB_GS_TY": "32"}])
+def test_gauss_seidel_variants_bit_exact(dk, oracle, env, monkeypatch):
+    """The other tile heights and the one-launch-per-time-step schedule give the same bits."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for np_, mx, my in ((10, 100, 70), (2, 70, 45), (10, 64, 130)):
+        ns = 2 * np_
+        b = np.random.default_rng(3).standard_normal(ns * mx * my)
+        got = _gpu_psol(dk, np_, mx, my, 2, 2.5e3, b)
+        oracle.L.o_web_setpar(np_, mx, my)
+        z, x = b.copy(), np.zeros_like(b)
+        oracle.L.o_web_gauss_seidel(b.size, 1.0 / 2.5e3, z.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(got, z)
+
+
 def test_gauss_seidel_is_an_approximate_inverse(dk):
     """Property at a size the oracle is not needed for: A_S * GS(b) ~ b, A_S = I - (1/cj) J_diffusion."""
     np_, mx, my, cj = 10, 256, 192, 4.0e5
