@@ -336,15 +336,16 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
     gs_step_kernel<NS, SPC><<<ntile * (NS / SPC), 32 * SPC, smem, st>>>(a, t, z, x);
 }
 
-// Tuning notes (ns = 20, B200; profiles/README.md has the numbers).  One tile costs ~20 us on its SM whatever else
-// runs: 4 dependent rounds of loads (phase A), 63 wavefront steps of ~170 clk (phase B: LDS -> DMUL -> DADD -> DADD ->
-// STS) and 4 rounds of loads/stores (phase C), with 20 warps per SM to hide the latencies (issue slots are 1/3 used, the
-// dominant stall is long-scoreboard).  On a 1024x1024 mesh the sweep is 71 launches of <= 148 tiles, i.e. latency-bound;
-// on 4096x4096 it is 263 launches of up to 640 tiles and runs at ~2.7 TB/s of algorithmic traffic.  Tried without
-// gain: two CTAs per tile with half of the species each (same number of warps per SM), 16- and 32-row load batches
-// (register pressure at 640 threads), 16-row tiles (longer wavefront ramps, more launches).  The next step is a
-// persistent CTA per column strip with TMA double-buffered tiles, so that loads, wavefront and stores of
-// consecutive tiles overlap.
+// Tuning notes (ns = 20, B200; profiles/README.md has the numbers).  One 32x32 tile costs ~20 us on its SM (30 us when
+// all SMs stream at once): 4 dependent rounds of loads (phase A), 63 wavefront steps of ~170 clk (phase B: LDS -> DMUL
+// -> DADD -> DADD -> STS; DADD/DMUL 9 clk, STS->LDS 34 clk, the rest is issue: 20 warps x 17 instructions per step) and
+// 4 rounds of loads/stores (phase C); issue slots are 1/3 used, the dominant stall is long-scoreboard.
+//   one launch per time step : 1.74 ms (1024^2), 19.9 ms (4096^2)   -- first version, DKB_GS_PER_STEP=1
+//   persistent scheduler     : 1.56 ms (32x16 tiles, 2 CTAs/SM), 16.9 ms (32x32 tiles) = 3.2 TB/s algorithmic
+// Tried without gain: two CTAs per tile with half of the species each (same number of warps per SM), 16- and 32-row
+// load batches (register pressure at 640 threads), a branch-free wavefront body (idle lanes computing costs more than
+// the branch).  The next step is TMA double-buffering inside the persistent CTA so that the loads of the next tile
+// and the stores of the previous one overlap the wavefront.
 static int gs_spc(int ns)
 {
     static int knob = -1;   // DKB_GS_SPLIT=1: two CTAs per tile (half of the species each), tuning runs
