@@ -346,16 +346,6 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 // load batches (register pressure at 640 threads), a branch-free wavefront body (idle lanes computing costs more than
 // the branch).  The next step is TMA double-buffering inside the persistent CTA so that the loads of the next tile
 // and the stores of the previous one overlap the wavefront.
-static int gs_spc(int ns)
-{
-    static int knob = -1;   // DKB_GS_SPLIT=1: two CTAs per tile (half of the species each), tuning runs
-    if (knob < 0) {
-        const char *e = getenv("DKB_GS_SPLIT");
-        knob = e ? atoi(e) : 0;
-    }
-    return (knob == 1 && ns % 4 == 0) ? ns / 2 : ns;
-}
-
 // z := (approximately) A_S^-1 z, x = N words of scratch.
 // Several ranks: the sweep is lexicographic, so slab r would have to wait for slab r-1.  Instead every rank sweeps
 // its own slab extended by GS_OV_BELOW rows of the slab below and GS_OV_ABOVE rows of the slab above (one exchange
@@ -415,7 +405,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         a.gamma1[i] = hl0 * wp.coy[i] * elamda;
         a.dinv[i] = elamda;
     }
-    const int spc = gs_spc(wp.ns);
+    const int spc = wp.ns;   // species per CTA (a split over several CTAs was tried, see the notes above)
     // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
     const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
     // Tile height.  32 rows (one CTA per SM) move the fewest halo bytes and win when every SM has work all the time
@@ -423,7 +413,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
     // is dependency-bound (1.56 vs 1.79 ms at 1024x1024x20).  DKB_GS_TY overrides (tests, tuning).
     const char *ty_env = getenv("DKB_GS_TY");
     const int ty_want = ty_env ? std::max(1, std::min(32, atoi(ty_env))) : ((i64)a.mx * a.my <= (i64)3 << 20 ? 16 : 32);
-    int ty = (int)std::min<size_t>(ty_want, ((spc == wp.ns ? 200u : 110u) * 1024u) / rowbytes - 1);
+    int ty = (int)std::min<size_t>(ty_want, (200u * 1024u) / rowbytes - 1);
     ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
@@ -444,7 +434,8 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
     const int per_step = (ps_env && atoi(ps_env) == 1) ? 1 : 0;
 #define GS_CASES(M) \
     switch (wp.ns) { \
-        M(2) M(4) M(6) M(8) M(10) M(12) M(14) M(16) M(18) M(20) M(22) M(24) M(26) M(28) M(30) M(32) \
+        M(2) M(4) M(6) M(8) M(10) M(12) M(16) M(20) M(24) M(32) \
+        default: return dkb_fail(DKB_E_UNSUPPORTED, "Gauss-Seidel factor: ns=%d not instantiated (2,4,6,8,10,12,16,20,24,32)", wp.ns); \
     }
     if (!per_step) {
         // ---- one persistent launch: scheduler state (re)built when the tiling changes ----
@@ -497,7 +488,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         for (int t = 0; t < nt; ++t) {
             const int ntile = tiles_at(t);
             if (ntile == 0) continue;
-#define GS_L(n) case n: if (spc == n) gs_launch<n, n>(a, ntile, t, z, x, c->stream); else gs_launch<n, (n % 4 == 0 ? n / 2 : n)>(a, ntile, t, z, x, c->stream); break;
+#define GS_L(n) case n: gs_launch<n, n>(a, ntile, t, z, x, c->stream); break;
             GS_CASES(GS_L)
 #undef GS_L
             COUNT_LAUNCH();
