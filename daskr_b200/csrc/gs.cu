@@ -476,6 +476,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
             static int per_sm = 1; \
             if (smem != set) { \
                 cudaFuncSetAttribute(gs_persistent_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                cudaFuncSetAttribute(gs_persistent_kernel<n>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_persistent_kernel<n>, 32 * n, smem); \
                 per_sm = std::max(1, per_sm); \
                 set = smem; \
