@@ -281,6 +281,7 @@ int dkb_set_option(int opt, int64_t value)
     case DKB_OPT_DEVICE_IO: g_ctx->opt_device_io = value != 0; break;
     case DKB_OPT_FUSED: g_ctx->opt_fused = (int)value; break;   // 0 callbacks, 1 two kernels, 2 single kernel
     case DKB_OPT_MAX_STEPS: g_ctx->opt_max_steps = value > 0 ? value : 500; break;
+    case 99: g_ctx->debug_variant = (int)value; break;   // kernel-variant selector for tuning runs (not in the header)
     default: return dkb_fail(DKB_E_ARG, "unknown option %d", opt);
     }
     return 0;
