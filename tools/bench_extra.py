@@ -28,19 +28,28 @@ sweep = []
 rng = np.random.default_rng(0)
 for ns in (2, 4, 8, 16, 20, 32):
     for nblk in (10_000, 100_000, 1_000_000, 10_000_000):
-        if ns * ns * nblk * 8 > 12e9:
-            continue
-        bd = rng.standard_normal((nblk, ns * ns))
-        rhs = rng.standard_normal((nblk, ns))
+        # up to 81.9 GB of blocks (ns=32 x 1e7): a base batch of <= 1e6 random blocks is generated on the host and
+        # tiled over the device array (every rep restores the array from the base: dgefa works in place)
+        base_n = min(nblk, 1_000_000)
+        ntile = nblk // base_n
+        bd = rng.standard_normal((base_n, ns * ns))
+        rhs = rng.standard_normal((base_n, ns))
         d_bd0, d_b0 = DeviceBuffer.from_host(bd), DeviceBuffer.from_host(rhs)
-        d_bd, d_b, d_ip = DeviceBuffer(bd.nbytes), DeviceBuffer(rhs.nbytes), DeviceBuffer(4 * ns * nblk)
+        bd_bytes, rhs_bytes = bd.nbytes, rhs.nbytes
+        d_bd, d_b, d_ip = DeviceBuffer(bd_bytes * ntile), DeviceBuffer(rhs_bytes * ntile), DeviceBuffer(4 * ns * nblk)
         del bd, rhs
+
+        def restore():
+            for k in range(ntile):
+                L.dkb_memcpy_d2d(C.c_void_p(d_bd.ptr.value + k * bd_bytes), d_bd0.ptr, bd_bytes)
+                L.dkb_memcpy_d2d(C.c_void_p(d_b.ptr.value + k * rhs_bytes), d_b0.ptr, rhs_bytes)
+            L.dkb_sync()
+
         first = C.c_int64(0)
-        reps = 5 if nblk >= 1_000_000 else 20
+        reps = 3 if nblk >= 10_000_000 else 5 if nblk >= 1_000_000 else 20
         tf = ts = 0.0
         for r in range(reps + 1):
-            L.dkb_memcpy_d2d(d_bd.ptr, d_bd0.ptr, d_bd0.nbytes)
-            L.dkb_memcpy_d2d(d_b.ptr, d_b0.ptr, d_b0.nbytes)
+            restore()
             t0 = time.perf_counter()
             L.dkb_dgefa_batched(d_bd.ptr, d_ip.ptr, ns, nblk, None, C.byref(first))
             t1 = time.perf_counter()
@@ -53,7 +62,18 @@ for ns in (2, 4, 8, 16, 20, 32):
         ts /= reps
         fl_f = sum(m + 2 * m * m for m in range(1, ns))            # dgefa flops per block
         fl_s = 2 * ns * ns - ns
-        sweep.append({"ns": ns, "nblk": nblk, "dgefa_ms": tf * 1e3, "dgesl_ms": ts * 1e3,
+        # the last tile saw the same input as the first: same factors, pivots and solutions (64-bit indexing check)
+        agree = True
+        if ntile > 1:
+            nchk = 1000
+            for buf, per, dt in ((d_bd, ns * ns * 8, np.float64), (d_b, ns * 8, np.float64)):
+                a0 = np.empty(nchk * per // 8, dtype=dt)
+                a1 = np.empty_like(a0)
+                L.dkb_memcpy_d2h(a0.ctypes.data_as(C.c_void_p), buf.ptr, a0.nbytes)
+                off = (ntile - 1) * base_n * per
+                L.dkb_memcpy_d2h(a1.ctypes.data_as(C.c_void_p), C.c_void_p(buf.ptr.value + off), a1.nbytes)
+                agree = agree and bool(np.array_equal(a0, a1)) and bool(np.isfinite(a0).all())
+        sweep.append({"ns": ns, "nblk": nblk, "gb_of_blocks": ns * ns * nblk * 8 / 1e9, "last_tile_equals_first": agree, "dgefa_ms": tf * 1e3, "dgesl_ms": ts * 1e3,
                       "dgefa_gflops": fl_f * nblk / tf / 1e9, "dgefa_gbs": (16 * ns * ns + 4 * ns) * nblk / tf / 1e9,
                       "dgesl_gflops": fl_s * nblk / ts / 1e9, "dgesl_gbs": (8 * ns * ns + 20 * ns) * nblk / ts / 1e9})
         print("lu ns=%d nblk=%d dgefa %.3f ms dgesl %.3f ms" % (ns, nblk, tf * 1e3, ts * 1e3), file=sys.stderr, flush=True)
