@@ -35,12 +35,25 @@ struct GsArgs {
     double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];   // beta2 = 2*beta1, gamma2 = 2*gamma1 (:452-455)
 };
 
+// Spin until a tile's done flag carries this application's epoch (persistent kernel only).
+__device__ __forceinline__ void gs_wait(const unsigned *flag, unsigned epoch)
+{
+    unsigned v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == epoch) break;
+        __nanosleep(64);
+    }
+}
+
 // One tile of one iteration.  IT1: first iteration (x = dinv*z, no U step, z := 0 + x).
 // Shared memory: (ty+1) rows x PITCH doubles; row 0 / point column 0 = lower / left halo.  PITCH = 33*NS + 1: the odd
 // pad makes the skewed accesses of phase B (row s-lane, column lane) hit 32 different banks.
 template <int NS, int SPC, bool IT1>
 __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, double *__restrict__ z,
-                                        double *__restrict__ x, double *sm, int t)
+                                        double *__restrict__ x, double *sm, int t,
+                                        const unsigned *wait_left = nullptr, const unsigned *wait_below = nullptr,
+                                        unsigned *edge_flag = nullptr, unsigned epoch = 0)
 {
 #ifdef GS_DEBUG_CLOCKS
     const bool dbg = blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && t < 256;
@@ -68,14 +81,6 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
 
     // ---- phase A: right-hand side of the triangular solve for every point of the tile, and the halos ----
     {
-        // halo loads first (into registers): in flight together with the first batch
-        double hl[2] = {0.0, 0.0}, hb = 0.0;                       // left halo: up to 64 rows = 2 per thread
-        const bool has_hb = jy0 > 0 && mine;
-#pragma unroll
-        for (int k = 0; k < 2; ++k)                               // this iteration's values of the left tile
-            if (jx0 > 0 && q + 32 * k < hgt) hl[k] = __ldcg(&x[(i64)(jy0 + q + 32 * k) * mxns + (i64)(jx0 - 1) * NS + g0 + i]);
-        if (has_hb) hb = __ldcg(&x[col0 - mxns]);                         // ... and of the tile below
-
         const double b1 = a.beta1[g0 + ic], g1 = a.gamma1[g0 + ic], dinv = a.dinv[g0 + ic];
         const double betU = (jx == 1) ? 2 * b1 : b1;              // (D-inverse)*U*x (:486-530)
         const bool has_right = jx < mx;
@@ -117,11 +122,21 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             }
             if (mine) smp[r0 * PITCH] = uu;
         }
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-            if (jx0 > 0 && q + 32 * k < hgt) sm[(q + 32 * k + 1) * PITCH + i] = hl[k];
-        if (has_hb) sm[SPC + tid] = hb;
     }
+    // ---- halos: this sweep's values of the tile to the left and of the tile below.  In the persistent kernel those two
+    // tiles are waited for only here: everything above needs the PREVIOUS sweep only, so it is off the critical path.
+    if (wait_left || wait_below) {
+        if (tid == 0) {
+            if (wait_left) gs_wait(wait_left, epoch);
+            if (wait_below) gs_wait(wait_below, epoch);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)                                   // left halo: up to 64 rows = 2 per thread
+        if (jx0 > 0 && q + 32 * k < hgt)
+            sm[(q + 32 * k + 1) * PITCH + i] = __ldcg(&x[(i64)(jy0 + q + 32 * k) * mxns + (i64)(jx0 - 1) * NS + g0 + i]);
+    if (jy0 > 0 && mine) sm[SPC + tid] = __ldcg(&x[col0 - mxns]);
 
     GS_CLK(1);
     // z of the first UC rows for phase C: in flight while phase B runs
@@ -183,6 +198,23 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
     GS_CLK(3);
     __syncthreads();
     GS_CLK(4);
+    // Persistent kernel: the right column and the top row are all that the neighbours of THIS sweep need.  Write them
+    // first and flag them, so that the tiles to the right and above start their wavefront while phase C streams.
+    if (edge_flag) {
+        for (int e = tid; e < hgt * SPC; e += blockDim.x) {
+            const int r = e / SPC, ii = e - r * SPC;
+            x[(i64)(jy0 + r) * mxns + (i64)(jx0 + w - 1) * NS + g0 + ii] = sm[(r + 1) * PITCH + w * SPC + ii];
+        }
+        for (int e = tid; e < w * SPC; e += blockDim.x) {
+            const int qq = e / SPC, ii = e - qq * SPC;
+            x[(i64)(jy0 + hgt - 1) * mxns + (i64)(jx0 + qq) * NS + g0 + ii] = sm[hgt * PITCH + (qq + 1) * SPC + ii];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(edge_flag), "r"(epoch) : "memory");
+        }
+    }
 
     // ---- phase C: x out, z := z + x (:568-570; z was zeroed before the first iteration, :478) ----
     {
@@ -248,30 +280,25 @@ __global__ void __launch_bounds__(32 * SPC) gs_step_kernel(const __grid_constant
 
 // ---- persistent variant: one launch per application ----
 // The tiles are numbered in the order of the launch schedule above (time step, then sweep, then column), and the
-// CTAs of ONE launch take them from an atomic ticket counter.  Before working on a tile a CTA waits for the four
-// tiles it depends on -- (I-1,J) and (I,J-1) of its own sweep, (I+1,J) and (I,J+1) of the previous sweep -- to be
-// flagged done.  All of them have smaller numbers, so they have been taken by CTAs that are running (a CTA only takes
-// a ticket when it is resident): the tile with the smallest unfinished number never waits, and the sweep cannot
-// deadlock whatever the number of resident CTAs.  What this buys over one launch per time step: no grid-wide
-// barrier per step, no partial waves -- an SM starts its next tile as soon as that tile's own inputs exist.
+// CTAs of ONE launch take them from an atomic ticket counter.  A tile (I,J) of sweep k needs
+//   (I+1,J), (I,J+1) and (I,J) of sweep k-1, complete ("done" flag)      -- before its U step (phase A),
+//   the right column of (I-1,J) and the top row of (I,J-1) of sweep k    -- before its wavefront (phase B);
+// the second pair is waited for only after phase A, and a tile publishes its right column and top row ("edge" flag)
+// right after its wavefront, before phase C streams the rest: along the chain of dependent tiles only the halo
+// load, the wavefront and the edge store are serial.  All dependencies have smaller numbers, so they have been taken
+// by CTAs that are running (a CTA only takes a ticket when it is resident): the tile with the smallest unfinished
+// number never waits, and the sweep cannot deadlock whatever the number of resident CTAs.  Write-after-read: a
+// tile overwrites x in phase C, after it has seen the edge flags of (I-1,J) and (I,J-1) -- the only readers of its
+// old values, in their phase A, which precedes their edge flag.
 // Loads of x and z go to L2 (__ldcg): L1 is not coherent between SMs inside a launch.
 struct GsSched {
     unsigned *ticket;          // next tile number
     unsigned *done;            // [GS_ITMAX][nty][ntx]: == epoch when the tile of this application is finished
+    unsigned *edge;            // same shape: == epoch when the tile's right column and top row are in memory
     const int *first;          // first[t] = number of tiles before time step t, first[nt] = total
     unsigned epoch;
     int nt, total;
 };
-
-__device__ __forceinline__ void gs_wait(const unsigned *flag, unsigned epoch)
-{
-    unsigned v;
-    for (;;) {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v == epoch) break;
-        __nanosleep(64);
-    }
-}
 
 template <int NS>
 __global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_constant__ GsArgs a, const GsSched s,
@@ -302,8 +329,7 @@ __global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_con
                 }
                 const unsigned *own = s.done + (size_t)(iter - 1) * a.nty * a.ntx;
                 const unsigned *prv = own - (size_t)a.nty * a.ntx;
-                if (I > 0) gs_wait(own + (size_t)J * a.ntx + I - 1, s.epoch);
-                if (J > 0) gs_wait(own + (size_t)(J - 1) * a.ntx + I, s.epoch);
+                // (I-1,J) and (I,J-1) of this sweep are waited for inside the tile, after its U step
                 if (iter > 1 && I < a.ntx - 1) gs_wait(prv + (size_t)J * a.ntx + I + 1, s.epoch);
                 if (iter > 1 && J < a.nty - 1) gs_wait(prv + (size_t)(J + 1) * a.ntx + I, s.epoch);
                 if (iter > 1) gs_wait(prv + (size_t)J * a.ntx + I, s.epoch);   // the tile's own previous sweep (x, z in place)
@@ -313,8 +339,12 @@ __global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_con
         __syncthreads();
         const int iter = cur[0], I = cur[1], J = cur[2], tt = cur[3];
         if (iter == 0) return;
-        if (iter == 1) gs_tile<NS, NS, true>(a, I, J, 0, z, x, sm, tt);
-        else gs_tile<NS, NS, false>(a, I, J, 0, z, x, sm, tt);
+        unsigned *own = s.edge + (size_t)(iter - 1) * a.nty * a.ntx;
+        const unsigned *wl = I > 0 ? own + (size_t)J * a.ntx + I - 1 : nullptr;
+        const unsigned *wb = J > 0 ? own + (size_t)(J - 1) * a.ntx + I : nullptr;
+        unsigned *ef = own + (size_t)J * a.ntx + I;
+        if (iter == 1) gs_tile<NS, NS, true>(a, I, J, 0, z, x, sm, tt, wl, wb, ef, s.epoch);
+        else gs_tile<NS, NS, false>(a, I, J, 0, z, x, sm, tt, wl, wb, ef, s.epoch);
         __syncthreads();       // every thread's stores are issued; shared memory is free for the next tile
         if (threadIdx.x == 0) {
             __threadfence();
@@ -341,7 +371,8 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 // -> DADD -> DADD -> STS; DADD/DMUL 9 clk, STS->LDS 34 clk, the rest is issue: 20 warps x 17 instructions per step) and
 // 4 rounds of loads/stores (phase C); issue slots are 1/3 used, the dominant stall is long-scoreboard.
 //   one launch per time step : 1.74 ms (1024^2), 19.9 ms (4096^2)   -- first version, DKB_GS_PER_STEP=1
-//   persistent scheduler     : 1.56 ms (32x16 tiles, 2 CTAs/SM), 16.9 ms (32x32 tiles) = 3.2 TB/s algorithmic
+//   persistent scheduler     : 1.56 ms, 16.9 ms
+//   + late waits, early edges: 1.2 ms (2.8 TB/s algorithmic), 17.4 ms (3.1 TB/s); per tile A ~15k, B ~11k, C ~12k clk
 // Tried without gain: two CTAs per tile with half of the species each (same number of warps per SM), 16- and 32-row
 // load batches (register pressure at 640 threads), a branch-free wavefront body (idle lanes computing costs more than
 // the branch).  The next step is TMA double-buffering inside the persistent CTA so that the loads of the next tile
@@ -408,11 +439,9 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
     const int spc = wp.ns;   // species per CTA (a split over several CTAs was tried, see the notes above)
     // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
     const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
-    // Tile height.  32 rows (one CTA per SM) move the fewest halo bytes and win when every SM has work all the time
-    // (17 vs 20 ms at 4096x4096x20); 16 rows (two CTAs per SM, shorter tiles on the critical path) win when the sweep
-    // is dependency-bound (1.56 vs 1.79 ms at 1024x1024x20).  DKB_GS_TY overrides (tests, tuning).
+    // Tile height: 32 rows (fewest halo bytes, shortest chain of tiles).  DKB_GS_TY overrides (tests, tuning).
     const char *ty_env = getenv("DKB_GS_TY");
-    const int ty_want = ty_env ? std::max(1, std::min(32, atoi(ty_env))) : ((i64)a.mx * a.my <= (i64)3 << 20 ? 16 : 32);
+    const int ty_want = ty_env ? std::max(1, std::min(32, atoi(ty_env))) : 32;
     int ty = (int)std::min<size_t>(ty_want, (200u * 1024u) / rowbytes - 1);
     ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
@@ -448,10 +477,10 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
             std::vector<int> first(nt + 1, 0);
             for (int t = 0; t < nt; ++t) first[t + 1] = first[t] + tiles_at(t);
             const size_t nflag = (size_t)GS_ITMAX * a.ntx * a.nty;
-            if (cudaMalloc(&c->gs_ticket, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->gs_done, sizeof(unsigned) * nflag) != cudaSuccess ||
+            if (cudaMalloc(&c->gs_ticket, sizeof(unsigned)) != cudaSuccess || cudaMalloc(&c->gs_done, sizeof(unsigned) * 2 * nflag) != cudaSuccess ||
                 cudaMalloc(&c->gs_first, sizeof(int) * (nt + 1)) != cudaSuccess)
                 return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the scheduler state");
-            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * nflag, c->stream);
+            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * 2 * nflag, c->stream);   // done flags, then edge flags
             cudaMemcpyAsync(c->gs_first, first.data(), sizeof(int) * (nt + 1), cudaMemcpyHostToDevice, c->stream);
             cudaStreamSynchronize(c->stream);   // `first` is a local
             c->gs_ntx = a.ntx;
@@ -462,11 +491,11 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         }
         c->gs_epoch += 1;
         if (c->gs_epoch == 0) {   // wrapped: flags of 2^32 applications ago could alias
-            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * (size_t)GS_ITMAX * a.ntx * a.nty, c->stream);
+            cudaMemsetAsync(c->gs_done, 0, sizeof(unsigned) * 2 * (size_t)GS_ITMAX * a.ntx * a.nty, c->stream);
             c->gs_epoch = 1;
         }
         cudaMemsetAsync(c->gs_ticket, 0, sizeof(unsigned), c->stream);
-        GsSched sch{c->gs_ticket, c->gs_done, c->gs_first, c->gs_epoch, c->gs_nt, c->gs_total};
+        GsSched sch{c->gs_ticket, c->gs_done, c->gs_done + (size_t)GS_ITMAX * a.ntx * a.nty, c->gs_first, c->gs_epoch, c->gs_nt, c->gs_total};
         const size_t smem = rowbytes * (a.ty + 1);
         static int nsm = 0;
         if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);

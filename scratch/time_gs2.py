@@ -25,3 +25,11 @@ t0 = time.perf_counter()
 for _ in range(20): call()
 L.dkb_sync()
 print("GS %dx%dx20: %%.3f ms per application" % (mx, my) % ((time.perf_counter() - t0) / 20 * 1e3))
+import ctypes
+if hasattr(L, "dkb_debug_gs_clocks"):
+    out = (ctypes.c_longlong * 2048)()
+    call(); L.dkb_debug_gs_clocks(out)
+    v = list(out)
+    for t in range(0, 72, 6):
+        w = v[t*8:t*8+6]
+        if w[0]: print("t=%d: A %d  wait+halo+zin %d  B %d  sync %d  edge+C %d  total %d cycles" % (t, w[1]-w[0], w[2]-w[1], w[3]-w[2], w[4]-w[3], w[5]-w[4], w[5]-w[0]))
