@@ -30,5 +30,16 @@ rng = np.random.default_rng(0)
 bd = rng.standard_normal((4, 25))
 _, ip, _ = o.dgefa_batched(bd, 5)
 out["dgefa5"] = {"ipvt": ip.tolist()}
+# the shipped preconditioner settings: spatial Gauss-Seidel factor (jpre = 3), block grouping (5 x 5 groups), root
+r3 = o.run_web(1, 20, 20, touts, jpre=3)
+out["web20_jpre3"] = {"c1_average": [float(y.reshape(20, 20, 2)[:, :, 0].mean()) for y in r3["y"]],
+                      "counters_last": r3["counters"][-1][[10, 11, 12, 18, 19, 20]].tolist()}
+rg = o.run_web(1, 20, 20, touts, jpre=3, nxg=5, nyg=5)
+out["web20_jpre3_groups5"] = {"c1_average": [float(y.reshape(20, 20, 2)[:, :, 0].mean()) for y in rg["y"]],
+                              "counters_last": rg["counters"][-1][[10, 11, 12, 18, 19, 20]].tolist()}
+from tests.test_gpu_roots import oracle_web_roots  # noqa: E402  (CPU helper living next to the GPU test)
+rr = oracle_web_roots(o, 1, 20, 20, [1e-8, 1e-6, 1e-4, 1e-2, 1e-1])
+out["web20_root"] = {"t": [t for t, _, _ in rr["roots"]], "jroot": [j.tolist() for _, j, _ in rr["roots"]],
+                     "nst_at_root": [int(c[10]) for _, _, c in rr["roots"]]}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_golden.json"), "w"), indent=1)
 print("wrote oracle_golden.json")
