@@ -59,6 +59,53 @@ def main():
             print("%s np=%d %dx%d fused=%s jpre=%d groups=%d world=%d: max wrms(diff)/tol=%.3e  NST %d/%d NNI %d/%d NLI %d/%d NJE %d/%d -> %s"
                   % (kind, np_, mx, my, fused, jpre, ng, world, err.max(), cg[10], co[10], cg[18], co[18], cg[19], co[19], cg[12], co[12],
                      "OK" if good else "FAIL"), flush=True)
+    # ---- rootfinding across slabs: the root function is an all-reduced device sum (example_web.f90:577-617) ----
+    touts = [1e-6, 1e-4, 1e-2, 5e-2]
+    g = dk.solve_web(1, 20, 22, touts, roots=True)
+    if rank == 0:
+        from tests import oracle_py
+        from tests.test_gpu_roots import oracle_web_roots
+
+        o = oracle_web_roots(oracle_py.load(), 1, 20, 22, touts)
+        good = len(g["roots"]) == len(o["roots"]) == 1 and abs(g["roots"][0][0] - o["roots"][0][0]) <= 1e-9 * o["roots"][0][0] \
+            and g["roots"][0][1][0] == o["roots"][0][1][0] and g["roots"][0][2][10] == o["roots"][0][2][10]
+        ok = ok and good
+        print("roots world=%d: t_root %.12e / %.12e jroot %d/%d NST %d/%d -> %s" % (
+            world, g["roots"][0][0], o["roots"][0][0], g["roots"][0][1][0], o["roots"][0][1][0], g["roots"][0][2][10],
+            o["roots"][0][2][10], "OK" if good else "FAIL"), flush=True)
+
+    # ---- checkpoint / continuation with one state buffer per rank ----
+    def run(break_after):
+        probe = np.zeros(64, dtype=np.int32)
+        dk.setup_rbdpre(24, 26, 2, 1, 0, probe)
+        _, myloc = dk.slab()
+        neq = 2 * 24 * myloc
+        iwork = np.zeros(40 + neq, dtype=np.int32)
+        dk.setup_rbdpre(24, 26, 2, 1, 40, iwork)
+        dk.web_setpar(1, 24, 26)
+        info = np.zeros(20, dtype=np.int32)
+        info[[10, 11, 13, 14, 15]] = 1
+        rwork, rpar, ipar = np.zeros(60), np.zeros(1), np.array([3, 0], dtype=np.int32)
+        c, cdot = dk.web_cinit(neq)
+        t, idid = dk.daskr(dk.WEB_RES, neq, 0.0, c, cdot, 1e-6, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
+        info[10] = 0
+        outs = []
+        for k, tout in enumerate([1e-6, 1e-4, 1e-3, 1e-2]):
+            if k == break_after:
+                state = dk.state_export()
+                dk.web_setpar(1, 24, 26)          # (the communicator lives on: same process, state dropped and restored)
+                dk.state_import(state)
+            t, idid = dk.daskr(dk.WEB_RES, neq, t, c, cdot, tout, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
+            outs.append((c.copy(), iwork[:40].copy()))
+        return outs
+
+    a, b = run(None), run(2)
+    same = all(np.array_equal(x[0], y[0]) and np.array_equal(x[1], y[1]) for x, y in zip(a, b))
+    st = torch.tensor([1 if same else 0])
+    dist.all_reduce(st, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("state export/import world=%d: continuation bitwise %s" % (world, "OK" if st.item() == 1 else "FAIL"), flush=True)
+        ok = ok and st.item() == 1
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
     dist.barrier()
