@@ -602,6 +602,28 @@ static void k_dlinsk(DkbCtx *c, const Cb &cb, double t, double cj, double tscale
     f1norm = ((*fnorm) * (*fnorm)) / 2;
     ratio = 1.0;
     rl = 1.0;
+    // constraint violations rescale the step until there is none (:2486-2504); rlx = 0.4 (dnsik:2276)
+    if (c->s_icnflg != 0) {
+        const double rlx = 0.4, fac = 0.6, fac2 = 0.9;
+        double tau = *pnorm;
+        for (;;) {
+            v_dyypnw(neq, c->y, c->yp, cj, rl, p, icopt, c->d_id, ynew, ydotnew);
+            double rr[2];
+            r_cnstr(neq, c->y, ynew, c->d_icnstr, 46);
+            scal_fetch(46, 2, rr);
+            if (rr[1] > 0.0) tau = fac * tau;                          // a hard violation (dcnstr:611-649)
+            else if (rr[0] >= rlx) tau = fac2 * tau * rlx / rr[0];     // too large a relative change (:654-657)
+            else break;
+            const double ratio1 = tau / (*pnorm);
+            ratio = ratio * ratio1;
+            v_scale(neq, ratio1, p);
+            *pnorm = tau;
+            if (*pnorm <= stptol) {
+                *iret = 1;
+                return;
+            }
+        }
+    }
     slpi = -2 * f1norm * ratio;
     rlmin = stptol / (*pnorm);
 
@@ -1149,7 +1171,6 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
     if (INFO[12] != 1) { why = "only the Krylov option info(12)=1 is implemented on device"; goto L701; }
     if (nrt < 0) { why = "nrt < 0"; goto L701; }
     if (nrt > 0 && rt == nullptr) { why = "nrt > 0 needs an rt routine (device arrays)"; goto L701; }
-    if (INFO[10] == 1 || INFO[10] == 3) { why = "constraint checking info(10)=1,3 not implemented on device"; goto L701; }
     if (c->rbd_set && neq != (i64)c->ns * c->npts) { why = "neq does not match setup_rbdpre slab (ns*mx*myloc)"; goto L701; }
 
     mxord = 5;
@@ -1159,9 +1180,10 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
     }
     IW[LMXORD] = mxord;
 
-    c->s_icnflg = 0;
-    c->s_nonneg = (INFO[10] == 2) ? 1 : 0;
-    c->s_lid = LICNS;
+    // info(10): 0 none, 1 constraints in the IC calculation, 2 non-negativity in the integration, 3 both (daskr.f:1477-1494)
+    c->s_icnflg = (INFO[10] == 1 || INFO[10] == 3) ? 1 : 0;
+    c->s_nonneg = (INFO[10] == 2 || INFO[10] == 3) ? 1 : 0;
+    c->s_lid = (c->s_icnflg != 0) ? LICNS + neq : LICNS;
 
     IW[LMITER] = INFO[12];
     if (INFO[13] == 0) {
@@ -1189,7 +1211,7 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
     }
 
     // work-array lengths: scalar headers only (the vector segments are device memory)
-    lenic = 0;
+    lenic = (c->s_icnflg != 0) ? neq : 0;
     c->s_lenid = 0;
     if (INFO[11] == 1 || INFO[16] == 1) c->s_lenid = (int)neq;
     c->s_ncphi = mxord + 1;
@@ -1203,7 +1225,7 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
     if (*lrw < lenrw) { why = "rwork too short (need 60 + 3*nrt)"; goto L701; }
     if (*liw < leniw) { why = "iwork too short (need 40 + lenic + lenid)"; goto L701; }
 
-    if (alloc_solver(c, neq, (int)maxl, IW[LKMP], INFO[16], c->s_lenid > 0, 0, INFO[2], IW[LLNWP], IW[LLNIWP]) != 0) {
+    if (alloc_solver(c, neq, (int)maxl, IW[LKMP], INFO[16], c->s_lenid > 0, lenic > 0, INFO[2], IW[LLNWP], IW[LLNIWP]) != 0) {
         why = c->err;
         goto L701;
     }
@@ -1216,6 +1238,14 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
         c->neq_g = (i64)(ng + 0.5);
     }
 
+    // ICNSTR legality (daskr.f:1608-1615); the consistency of y with it (dcnst0) is checked once y is on the device
+    if (lenic > 0) {
+        for (i64 ii = 1; ii <= neq; ++ii) {
+            const int ici = IW[LICNS - 1 + ii];
+            if (ici < -2 || ici > 2) { why = "ICNSTR entries must be in -2..2"; goto L701; }
+        }
+        cudaMemcpyAsync(c->d_icnstr, &IW[LICNS], sizeof(int) * neq, cudaMemcpyHostToDevice, c->stream);
+    }
     index = 1;
     if (c->s_lenid > 0) {
         index = 0;
@@ -1253,6 +1283,20 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
         const cudaMemcpyKind kind = c->opt_device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
         cudaMemcpyAsync(c->y, y, nb, kind, c->stream);
         cudaMemcpyAsync(c->yp, yprime, nb, kind, c->stream);
+    }
+    if (lenic > 0) {   // dcnst0 (daskr.f:1617-1622): the initial y must satisfy the constraints
+        c->h_iflag[0] = INT_MAX;
+        cudaMemcpyAsync(c->d_iflag, c->h_iflag, sizeof(int), cudaMemcpyHostToDevice, c->stream);
+        v_cnst0(neq, c->y, c->d_icnstr, c->d_iflag);
+        cudaMemcpyAsync(c->h_iflag, c->d_iflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        double bad = (c->h_iflag[0] != INT_MAX) ? 1.0 : 0.0;
+        if (c->nranks > 1) {   // every rank must take the same branch
+            cudaMemcpyAsync(c->d_scal + 50, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+            allreduce_max(50, 1);
+            scal_fetch(50, 1, &bad);
+        }
+        if (bad != 0.0) { why = "the initial y violates a constraint in ICNSTR"; goto L701; }
     }
     goto L200;
 

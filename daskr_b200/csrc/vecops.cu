@@ -455,6 +455,53 @@ void r_max(i64 n, const double *x, int slot)
     launch_reduce<0, 1>(RMaxVal{x}, n, slot);
     allreduce_max(slot, 1);
 }
+// dcnstr, src/daskr_new.f90:569-661, as one reduction.  The reference scans the unknowns in order, returns at the first
+// hard violation (tau = 0.6*tau) and otherwise compares the largest relative change rdymx of the |icnstr| = 2 unknowns
+// with rlx.  Both outcomes are order-free: "is there a hard violation" (a max over 0/1 flags) and rdymx (a max).
+struct RCnstr {
+    const double *y, *ynew;
+    const int *icn;
+    __device__ void init() {}
+    __device__ void operator()(i64 i, double (&a)[2]) const
+    {
+        const int ic = icn[i];
+        if (ic == 0) return;
+        const double yn = ynew[i];
+        bool hard;
+        if (ic == 2 || ic == -2) {
+            const double yi = y[i];
+            a[0] = fmax(a[0], fabs((yn - yi) / yi));
+            hard = (ic == 2) ? (yn <= 0.0) : (yn >= 0.0);
+        } else {
+            hard = (ic == 1) ? (yn < 0.0) : (yn > 0.0);
+        }
+        if (hard) a[1] = fmax(a[1], 1.0);
+    }
+};
+void r_cnstr(i64 n, const double *y, const double *ynew, const int *icnstr, int slot)
+{
+    launch_reduce<0, 2>(RCnstr{y, ynew, icnstr}, n, slot);   // [rdymx, hard-violation flag], both maxima (-DBL_MAX if none)
+    allreduce_max(slot, 2);
+}
+
+// dcnst0, src/daskr_new.f90:663-713: is the initial y consistent with the constraints?  flag = smallest violating
+// index + 1 (INT_MAX if none), as the reference's scan would find it.
+__global__ void cnst0_kernel(i64 n, const double *__restrict__ y, const int *__restrict__ icn, int *flag)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int ic = icn[i];
+        const double yi = y[i];
+        const bool bad = (ic == 2 && yi <= 0.0) || (ic == 1 && yi < 0.0) || (ic == -1 && yi > 0.0) || (ic == -2 && yi >= 0.0);
+        if (bad) atomicMin(flag, (int)(i < 2147483646 ? i + 1 : 2147483646));
+    }
+}
+void v_cnst0(i64 n, const double *y, const int *icnstr, int *d_flag)
+{
+    cnst0_kernel<<<red_grid(n), DKB_RED_BLOCK, 0, g_ctx->stream>>>(n, y, icnstr, d_flag);
+    COUNT_LAUNCH();
+}
+
 void r_dot(i64 n, const double *x, const double *y, int slot)
 {
     launch_reduce<1, 0>(RDot{x, y}, n, slot);
