@@ -353,6 +353,17 @@ def run_ours(args):
             roof["traffic_source"] = tr[key].get("source")
     except Exception:
         pass
+    # K5 (jac_rbdpre: FD block + LU) is the one compute-shaped kernel of the path: report FP64 rate.
+    # flops per mesh point: ns rblock evaluations of 2*ns^2 + 3*ns, one R0, LINPACK dgefa sum_m (m + 2 m^2)
+    jc = prof.get("jac", {"ms": 0.0, "count": 0})
+    if jc["count"] > 0 and jc["ms"] > 0:
+        fl_pt = (ns + 1) * (2 * ns * ns + 3 * ns) + sum(m + 2 * m * m for m in range(1, ns))
+        roof["jac_kernel"] = {"kernel": "web_jac2_kernel<20,16> (FD block Jacobian + LU, incl. the first-failure flag readback)",
+                              "calls": jc["count"], "avg_ms": jc["ms"] / jc["count"], "flops_per_point": fl_pt,
+                              "achieved_gflops": fl_pt * (neq // ns) / (jc["ms"] / jc["count"] * 1e-3) / 1e9,
+                              "fp64_peak_gflops": {"dfma": 33600.0, "dmul_dadd_pairs_no_fma": 18400.0,
+                                                   "source": "tools/fp64_peak.cu on this GPU type (profiles/README.md)"},
+                              "share_of_step_time": jc["ms"] / ms}
     phase_ms = {k: round(v["ms"], 3) for k, v in prof.items()}
 
     # =========== (2) e2e: same window through the host-buffer API, one call per step ===========

@@ -241,3 +241,18 @@ def test_fused_equals_unfused_bitwise_state(dk):
         # agrees to rounding, not bitwise, once Krylov iterations have happened
         assert np.allclose(runs[0]["c0"], runs[2]["c0"], rtol=1e-9, atol=1e-12)
         assert np.allclose(runs[0]["y"], runs[2]["y"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("ns", [1, 2, 5, 20, 32])
+def test_dgefa_dgesl_empty_and_single(dk, oracle, ns):
+    """Empty batch (no launch, no error) and a batch of one block."""
+    lu, ip, info, first = dk.dgefa_batched(np.zeros((0, ns * ns)), ns)
+    assert lu.shape[0] == 0 and ip.shape[0] == 0 and first == 0
+    x = dk.dgesl_batched(np.zeros((0, ns * ns)), np.zeros((0, ns), dtype=np.int32), np.zeros((0, ns)), ns)
+    assert x.shape[0] == 0
+    rng = np.random.default_rng(11)
+    bd, rhs = rng.standard_normal((1, ns * ns)), rng.standard_normal((1, ns))
+    lu_g, ip_g, info_g, first = dk.dgefa_batched(bd, ns)
+    lu_o, ip_o, info_o = oracle.dgefa_batched(bd, ns)
+    assert np.array_equal(lu_g, lu_o) and np.array_equal(ip_g, ip_o) and first == 0
+    assert np.array_equal(dk.dgesl_batched(lu_g, ip_g, rhs, ns), oracle.dgesl_batched(lu_o, ip_o, rhs, ns))
