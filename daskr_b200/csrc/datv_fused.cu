@@ -35,7 +35,11 @@ void datv_fused_upload_tables(const WebPar &p)
     cudaMemcpyToSymbol(c_coy, p.coy, sizeof(double) * p.ns);
 }
 
-template <int NS, int DF_TY, int MINB>
+// MODE 0: the whole of datv (perturbed residual, - savr, block solve, * wght).
+// MODE 1: the residual half only, vnext = G(y + v/wght, ydot + cj*v/wght) - savr   (datv with jpre = 3: the
+//         Gauss-Seidel factor runs between the residual and the block solve).
+// MODE 2: the plain residual, vnext = G(y, ydot)                                   (res, example_web.f90:190-224).
+template <int NS, int DF_TY, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(DF_TX * DF_TY, MINB)
 web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
                        const double *__restrict__ y, const double *__restrict__ ydot,
@@ -79,18 +83,23 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
             const i64 g = ok ? ((i64)gy * mxns + (i64)gx * NS + i) : gsafe;
             zo[u] = ok ? (zr * ZX + zx) * PZ + i : -1;
             yo[u] = okyd ? ((zr - 1) * DF_TX + (zx - 1)) * PY + i : -1;
-            rwt[u] = __ldg(wt + g);
-            rv[u] = __ldg(v + g);
+            rwt[u] = (MODE == 2) ? 1.0 : __ldg(wt + g);
+            rv[u] = (MODE == 2) ? 0.0 : __ldg(v + g);
             ry[u] = __ldg(y + g);
             ryd[u] = __ldg(ydot + (okyd ? g : gsafe));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (zo[u] >= 0) {
-                const double wgt = wscale * rwt[u];
-                const double vtmp = rv[u] / wgt;               // vtemp = v/wght
-                Z[zo[u]] = ry[u] + vtmp;                       // z = y + vtemp
-                if (yo[u] >= 0) YDT[yo[u]] = ryd[u] + vtmp * cj;   // ydottemp = ydot + vtemp*cj
+                if (MODE == 2) {
+                    Z[zo[u]] = ry[u];
+                    if (yo[u] >= 0) YDT[yo[u]] = ryd[u];
+                } else {
+                    const double wgt = wscale * rwt[u];
+                    const double vtmp = rv[u] / wgt;               // vtemp = v/wght
+                    Z[zo[u]] = ry[u] + vtmp;                       // z = y + vtemp
+                    if (yo[u] >= 0) YDT[yo[u]] = ryd[u] + vtmp * cj;   // ydottemp = ydot + vtemp*cj
+                }
             }
         }
     }
@@ -131,12 +140,16 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
             const double dcxli = ci - Z[pxl * PZ + k], dcxui = Z[pxu * PZ + k] - ci;
             const double f = c_coy[k] * (dcyui - dcyli) + c_cox[k] * (dcxui - dcxli) + R;   // f:264
             const double d = (k >= NPH) ? -f : (YDT[tid * PY + (k < NPH ? k : 0)] - f);      // res:215-219
-            b[k] = d - __ldg(savr + g0 + k);                                       // z = vtemp - savr
+            b[k] = (MODE == 2) ? d : d - __ldg(savr + g0 + k);                     // z = vtemp - savr
         }
     }
     __syncthreads();   // Z is free from here on (reused as the output staging buffer)
 
-    if (live) {
+    if (live && MODE != 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) Z[tid * PZ + i] = b[i];
+    }
+    if (live && MODE == 0) {
         // psol_rbdpre: dgesl with the LU block streamed from the interleaved layout
         const double *a = lut + ((p >> 5) * (NS * NS)) * 32 + lane;
         const int *pv = pt + ((p >> 5) * NS) * 32 + lane;
@@ -184,19 +197,19 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
             const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
             const int oy = y0 + r;
             go[m] = (oy < w.my) ? ((i64)oy * mxns + (i64)x0 * NS + rem) : -1;
-            rw[m] = __ldg(wt + (go[m] >= 0 ? go[m] : gsafe));
+            rw[m] = (MODE != 0) ? 1.0 : __ldg(wt + (go[m] >= 0 ? go[m] : gsafe));
         }
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
             const int idx = tid + m * DF_THREADS;
             const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
             const int q = r * DF_TX + rem / NS;
-            if (go[m] >= 0) vnext[go[m]] = Z[q * PZ + (rem % NS)] * (wscale * rw[m]);
+            if (go[m] >= 0) vnext[go[m]] = (MODE != 0) ? Z[q * PZ + (rem % NS)] : Z[q * PZ + (rem % NS)] * (wscale * rw[m]);
         }
     }
 }
 
-template <int NS, int DF_TY, int MINB>
+template <int NS, int DF_TY, int MINB, int MODE = 0>
 static bool launch_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
                           const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
                           double *vnext)
@@ -206,11 +219,11 @@ static bool launch_single(const WebDev &w, const double *v, const double *wt, do
     constexpr int PZ = NS + 1, PY = (NS / 2) | 1;
     const size_t sh = sizeof(double) * ((DF_TX + 2) * (DF_TY + 2) * PZ + DF_THREADS * PY);
     if (!attr_set) {
-        cudaFuncSetAttribute(web_datv_single_kernel<NS, DF_TY, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        cudaFuncSetAttribute(web_datv_single_kernel<NS, DF_TY, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         attr_set = true;
     }
     const int tiles = (w.mx / DF_TX) * ((w.my + DF_TY - 1) / DF_TY);
-    web_datv_single_kernel<NS, DF_TY, MINB><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    web_datv_single_kernel<NS, DF_TY, MINB, MODE><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
     g_ctx->launches++;
     return true;
 }
@@ -237,4 +250,19 @@ bool web_datv_single(const WebDev &w, const double *v, const double *wt, double 
         }
     default: return false;
     }
+}
+
+// The residual alone with the same staging: mode 1 = datv's perturbed residual minus savr, mode 2 = plain res.
+// Same eligibility as web_datv_single; the caller falls back to web_restile_kernel otherwise.
+bool web_resid_single(const WebDev &w, int mode, const double *v, const double *wt, double wscale, const double *y,
+                      const double *ydot, const double *savr, double cj, double *out)
+{
+    if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
+#define RS(N) case N: return mode == 1 ? launch_single<N, 4, 4, 1>(w, v, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out) \
+                                       : launch_single<N, 4, 4, 2>(w, v, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+    switch (w.ns) {
+        RS(2) RS(4) RS(8) RS(10) RS(12) RS(16) RS(20)
+    default: return false;
+    }
+#undef RS
 }

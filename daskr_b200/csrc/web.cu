@@ -324,6 +324,7 @@ static void restile_launch(const WebDev &w, const double *v, const double *wt, d
 void web_res_launch(const double *c, const double *cdot, double *delta)
 {
     WebDev w = make_webdev();
+    if (g_ctx->opt_fused >= 2 && web_resid_single(w, 2, nullptr, nullptr, 1.0, c, cdot, nullptr, 0.0, delta)) return;
 #define CALL(N) restile_launch<N, false>(w, nullptr, nullptr, 1.0, c, cdot, 0.0, nullptr, delta)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
@@ -427,9 +428,11 @@ int web_datv_fused(const double *v, const double *wt, double wscale, const doubl
     const double *sub = (jpre == 1) ? nullptr : savr;
     {
         ProfScope ps(PROF_RESDATV);
+        if (!(jpre != 1 && x->opt_fused >= 2 && web_resid_single(w, 1, v, wt, wscale, y, ydot, savr, cj, vtemp))) {
 #define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, sub, vtemp)
-        WEB_DISPATCH(w.ns, CALL)
+            WEB_DISPATCH(w.ns, CALL)
 #undef CALL
+        }
     }
     if (jpre != 1 && web_gauss_seidel(1.0 / cj, vtemp, x->wk) != 0) return -1;
     tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1);

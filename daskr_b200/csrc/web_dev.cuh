@@ -13,6 +13,9 @@ WebDev make_webdev();
 // copies acoef / bcoef / cox / coy into the constant bank the fused datv kernel reads them from
 void datv_fused_upload_tables(const WebPar &p);
 void jac2_upload_tables(const WebPar &p);
+// residual only, same staging as the single datv kernel (datv_fused.cu): mode 1 = perturbed - savr, 2 = plain res
+bool web_resid_single(const WebDev &w, int mode, const double *v, const double *wt, double wscale, const double *y,
+                      const double *ydot, const double *savr, double cj, double *out);
 // two-phase FD + LU block Jacobian (jac2.cu)
 bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
               int *d_first_flag);

@@ -81,7 +81,7 @@ def test_gauss_seidel_is_an_approximate_inverse(dk):
 WEB_TOUTS = [1e-8, 1e-7, 1e-6, 1e-5, 1e-4, 1e-3, 1e-2, 1e-1, 1.0]
 
 
-@pytest.mark.parametrize("jpre,mx", [(3, 20), (3, 40), (4, 20)])
+@pytest.mark.parametrize("jpre,mx", [(3, 20), (3, 40), (4, 20), (3, 32), (3, 64)])
 def test_solve_web_with_spatial_factor(dk, oracle, jpre, mx):
     """example_web.f90 as shipped uses jpre = 3 (A_S then A_R).  Same run on both sides."""
     g = dk.solve_web(1, mx, mx, WEB_TOUTS, jpre=jpre)

@@ -78,7 +78,8 @@ def _web_setup_gpu(dk, np_, mx, my):
     dk.web_setpar(np_, mx, my)
 
 
-@pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (1, 7, 5), (2, 9, 6), (4, 12, 10), (10, 16, 12), (16, 6, 5)])
+@pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (1, 7, 5), (2, 9, 6), (4, 12, 10), (10, 16, 12), (16, 6, 5),
+                                       (1, 32, 9), (10, 64, 13), (5, 32, 32), (8, 96, 7)])   # mx % 32 == 0: staged single-kernel residual
 def test_web_res_bit_exact(dk, oracle, np_, mx, my):
     from daskr_b200.api import DeviceBuffer, _ref
 
