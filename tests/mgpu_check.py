@@ -31,7 +31,8 @@ def main():
     # case agrees with the full-mesh CPU run to the integration tolerance only (counters may differ by a few)
     cases = [("web", 1, 24, 26, True, 1, 0), ("web", 1, 24, 26, False, 1, 0), ("web", 10, 16, 18, True, 1, 0),
              ("heat", 0, 30, 0, True, 1, 0), ("web", 1, 40, 44, True, 3, 0), ("web", 10, 36, 40, True, 3, 0),
-             ("web", 1, 40, 44, True, 3, 5), ("web", 2, 30, 33, True, 1, 4)]   # last column: block grouping, ng x ng groups
+             ("web", 1, 40, 44, True, 3, 5), ("web", 2, 30, 33, True, 1, 4),   # last column: block grouping, ng x ng groups
+             ("web", 2, 32, 36, True, 3, 0), ("web", 1, 64, 30, True, 1, 0)]   # mx % 32 == 0: single-kernel datv / residual
     for kind, np_, mx, my, fused, jpre, ng in cases:
         if kind == "web":
             touts = [1e-8, 1e-6, 1e-4, 1e-3, 1e-2]
