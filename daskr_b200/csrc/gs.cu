@@ -47,7 +47,8 @@ __device__ __forceinline__ void gs_wait(const unsigned *flag, unsigned epoch)
 }
 
 // One tile of one iteration.  IT1: first iteration (x = dinv*z, no U step, z := 0 + x).
-// Shared memory: (ty+1) rows x PITCH doubles; row 0 / point column 0 = lower / left halo.  PITCH = 33*NS + 1: the odd
+// Shared memory: (ty+2) rows x PITCH doubles; row 0 / point column 0 = lower / left halo of THIS sweep, row hgt+1 /
+// point column w+1 = upper / right neighbours of the PREVIOUS sweep (U step).  PITCH = 34*NS + 1: the odd
 // pad makes the skewed accesses of phase B (row s-lane, column lane) hit 32 different banks.
 template <int NS, int SPC, bool IT1>
 __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, double *__restrict__ z,
@@ -60,7 +61,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
     long long *const dbgp = gs_dbg + (t & 255) * 8;
 #endif
     GS_CLK(0);
-    constexpr int PITCH = (GS_TX + 1) * SPC + 1;
+    constexpr int PITCH = (GS_TX + 2) * SPC + 1;
     constexpr int UA = GS_U, UC = GS_U;   // g0 = first species of this CTA's group of SPC species
     const int mx = a.mx, my = a.my;
     const i64 mxns = a.mxns;
@@ -84,43 +85,61 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
         const double b1 = a.beta1[g0 + ic], g1 = a.gamma1[g0 + ic], dinv = a.dinv[g0 + ic];
         const double betU = (jx == 1) ? 2 * b1 : b1;              // (D-inverse)*U*x (:486-530)
         const bool has_right = jx < mx;
-        const double *src = IT1 ? z + col0 : x + col0 + (has_right ? NS : 0);   // clamped: no right neighbour at jx == mx
-        const i64 upo = mxns - (has_right ? NS : 0);              // from src to the upper neighbour of this point
-        int r0 = 0;
-        for (; r0 + UA <= hgt; r0 += UA, src += UA * mxns) {
-            double v1[UA], v2[UA];
+        if (IT1) {
+            const double *src = z + col0;
+            int r0 = 0;
+            for (; r0 + UA <= hgt; r0 += UA, src += UA * mxns) {
+                double v1[UA];
 #pragma unroll
-            for (int u = 0; u < UA; ++u) {
-                v1[u] = __ldcg(&src[u * mxns]);
-                if (!IT1) v2[u] = __ldcg(&src[u * mxns + ((edge && r0 + u == rtop) ? 0 : upo)]);   // no row above the last one
+                for (int u = 0; u < UA; ++u) v1[u] = __ldcg(&src[u * mxns]);
+#pragma unroll
+                for (int u = 0; u < UA; ++u)
+                    if (mine) smp[(r0 + u) * PITCH] = dinv * v1[u];       // x = dinv*z (:470-481)
             }
+            for (; r0 < hgt; ++r0, src += mxns) {                         // rows of a partial last batch
+                const double v1 = __ldcg(&src[0]);
+                if (mine) smp[r0 * PITCH] = dinv * v1;
+            }
+        } else {
+            // The previous sweep's x of the tile, of the row above it and of the column to its right go to shared
+            // memory once (each value is the right neighbour of one point and the upper neighbour of another), then
+            // the U step runs in place, bottom-up in batches of rows: read (registers), barrier, write.
+            const bool has_up = jy0 + hgt < my;
+            const int nrows = hgt + (has_up ? 1 : 0);
+            const double *src = x + col0;
+            for (int r0 = 0; r0 < nrows; r0 += UA) {
+                double v1[UA];
 #pragma unroll
-            for (int u = 0; u < UA; ++u) {
-                double uu;
-                if (IT1) {
-                    uu = dinv * v1[u];                            // x = dinv*z (:470-481)
-                } else {
-                    const double gam = (r0 + u == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
-                    const double t1 = betU * v1[u], t2 = gam * v2[u];
-                    const bool lasty = edge && r0 + u == rtop;
-                    uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
+                for (int u = 0; u < UA; ++u) v1[u] = __ldcg(&src[(i64)min(r0 + u, nrows - 1) * mxns]);
+#pragma unroll
+                for (int u = 0; u < UA; ++u)
+                    if (mine && r0 + u < nrows) smp[(r0 + u) * PITCH] = v1[u];
+            }
+            if (jx0 + w < mx)
+                for (int e = tid; e < hgt * SPC; e += blockDim.x) {
+                    const int rr = e / SPC, ii = e - rr * SPC;
+                    sm[(rr + 1) * PITCH + (w + 1) * SPC + ii] = __ldcg(&x[(i64)(jy0 + rr) * mxns + (i64)(jx0 + w) * NS + g0 + ii]);
                 }
-                if (mine) smp[(r0 + u) * PITCH] = uu;
+            __syncthreads();
+            for (int r0 = 0; r0 < hgt; r0 += UA) {
+                double v1[UA], v2[UA];
+#pragma unroll
+                for (int u = 0; u < UA; ++u) {
+                    const int r = min(r0 + u, hgt - 1);
+                    v1[u] = smp[r * PITCH + SPC];                          // x(p + 1)
+                    v2[u] = smp[(r + 1) * PITCH];                          // x(p + row); unused in the last mesh row
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < UA; ++u) {
+                    const int r = r0 + u;
+                    const double gam = (r == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
+                    const double t1 = betU * v1[u], t2 = gam * v2[u];
+                    const bool lasty = edge && r == rtop;
+                    const double uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
+                    if (mine && r < hgt) smp[r * PITCH] = uu;
+                }
             }
-        }
-        for (; r0 < hgt; ++r0, src += mxns) {                     // rows of a partial last batch
-            const double v1 = __ldcg(&src[0]);
-            double uu;
-            if (IT1) {
-                uu = dinv * v1;
-            } else {
-                const bool lasty = r0 == rtop;
-                const double v2 = __ldcg(&src[lasty ? 0 : upo]);
-                const double gam = (r0 == 0 && jy0 == 0 && a.bot_bnd) ? 2 * g1 : g1;
-                const double t1 = betU * v1, t2 = gam * v2;
-                uu = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
-            }
-            if (mine) smp[r0 * PITCH] = uu;
         }
     }
     // ---- halos: this sweep's values of the tile to the left and of the tile below.  In the persistent kernel those two
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_con
 template <int NS, int SPC>
 static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, cudaStream_t st)
 {
-    const size_t smem = ((size_t)(GS_TX + 1) * SPC + 1) * sizeof(double) * (a.ty + 1);
+    const size_t smem = ((size_t)(GS_TX + 2) * SPC + 1) * sizeof(double) * (a.ty + 2);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         cudaFuncSetAttribute(gs_step_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -438,11 +457,11 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
     }
     const int spc = wp.ns;   // species per CTA (a split over several CTAs was tried, see the notes above)
     // tile height: at most 32 rows, within 200 KB of the 227 KB of shared memory
-    const size_t rowbytes = ((size_t)(GS_TX + 1) * spc + 1) * sizeof(double);
+    const size_t rowbytes = ((size_t)(GS_TX + 2) * spc + 1) * sizeof(double);
     // Tile height: 32 rows (fewest halo bytes, shortest chain of tiles).  DKB_GS_TY overrides (tests, tuning).
     const char *ty_env = getenv("DKB_GS_TY");
     const int ty_want = ty_env ? std::max(1, std::min(32, atoi(ty_env))) : 32;
-    int ty = (int)std::min<size_t>(ty_want, (200u * 1024u) / rowbytes - 1);
+    int ty = (int)std::min<size_t>(ty_want, (200u * 1024u) / rowbytes - 2);
     ty = std::max(1, std::min(ty, a.my));
     a.ty = ty;
     a.ntx = (wp.mx + GS_TX - 1) / GS_TX;
@@ -496,7 +515,7 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         }
         cudaMemsetAsync(c->gs_ticket, 0, sizeof(unsigned), c->stream);
         GsSched sch{c->gs_ticket, c->gs_done, c->gs_done + (size_t)GS_ITMAX * a.ntx * a.nty, c->gs_first, c->gs_epoch, c->gs_nt, c->gs_total};
-        const size_t smem = rowbytes * (a.ty + 1);
+        const size_t smem = rowbytes * (a.ty + 2);
         static int nsm = 0;
         if (!nsm) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
         // as many CTAs as are resident at once (shared memory decides), fewer if there are fewer tiles
