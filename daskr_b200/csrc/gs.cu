@@ -107,12 +107,13 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             const bool has_up = jy0 + hgt < my;
             const int nrows = hgt + (has_up ? 1 : 0);
             const double *src = x + col0;
-            for (int r0 = 0; r0 < nrows; r0 += UA) {
-                double v1[UA];
+            constexpr int UL = 17;                                        // 33 rows = two rounds of loads in flight
+            for (int r0 = 0; r0 < nrows; r0 += UL) {
+                double v1[UL];
 #pragma unroll
-                for (int u = 0; u < UA; ++u) v1[u] = __ldcg(&src[(i64)min(r0 + u, nrows - 1) * mxns]);
+                for (int u = 0; u < UL; ++u) v1[u] = __ldcg(&src[(i64)min(r0 + u, nrows - 1) * mxns]);
 #pragma unroll
-                for (int u = 0; u < UA; ++u)
+                for (int u = 0; u < UL; ++u)
                     if (mine && r0 + u < nrows) smp[(r0 + u) * PITCH] = v1[u];
             }
             if (jx0 + w < mx)
@@ -392,6 +393,7 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 //   one launch per time step : 1.74 ms (1024^2), 19.9 ms (4096^2)   -- first version, DKB_GS_PER_STEP=1
 //   persistent scheduler     : 1.56 ms, 16.9 ms
 //   + late waits, early edges: 1.2 ms (2.8 TB/s algorithmic), 17.4 ms (3.1 TB/s); per tile A ~15k, B ~11k, C ~12k clk
+//   + x of the previous sweep staged once in shared memory, U step in place: 1.1 ms, 14.7 ms (3.7 TB/s)
 // Tried without gain: two CTAs per tile with half of the species each (same number of warps per SM), 16- and 32-row
 // load batches (register pressure at 640 threads), a branch-free wavefront body (idle lanes computing costs more than
 // the branch).  The next step is TMA double-buffering inside the persistent CTA so that the loads of the next tile
