@@ -54,7 +54,7 @@ template <int NS, int SPC, bool IT1>
 __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, double *__restrict__ z,
                                         double *__restrict__ x, double *sm, int t,
                                         const unsigned *wait_left = nullptr, const unsigned *wait_below = nullptr,
-                                        unsigned *edge_flag = nullptr, unsigned epoch = 0)
+                                        unsigned *edge_flag = nullptr, unsigned epoch = 0, bool last_sweep = false)
 {
 #ifdef GS_DEBUG_CLOCKS
     const bool dbg = blockIdx.x == gridDim.x / 2 && threadIdx.x == 0 && t < 256;
@@ -250,7 +250,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
 #pragma unroll
                 for (int u = 0; u < UC; ++u) {
                     const double v = sp[u * PITCH];
-                    xo[u * mxns] = v;
+                    if (!last_sweep) xo[u * mxns] = v;   // nobody reads x after the last sweep (the edges are out already)
                     zo[u * mxns] = zin0[u] + v;
                 }
             }
@@ -262,7 +262,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             for (int u = 0; u < UC; ++u) {
                 if (r0 + u < hgt) {
                     const double v = sp[u * PITCH];
-                    xo[u * mxns] = v;
+                    if (!last_sweep) xo[u * mxns] = v;   // nobody reads x after the last sweep (the edges are out already)
                     zo[u * mxns] = zin0[u] + v;
                 }
             }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(32 * NS) gs_persistent_kernel(const __grid_con
         const unsigned *wb = J > 0 ? own + (size_t)(J - 1) * a.ntx + I : nullptr;
         unsigned *ef = own + (size_t)J * a.ntx + I;
         if (iter == 1) gs_tile<NS, NS, true>(a, I, J, 0, z, x, sm, tt, wl, wb, ef, s.epoch);
-        else gs_tile<NS, NS, false>(a, I, J, 0, z, x, sm, tt, wl, wb, ef, s.epoch);
+        else gs_tile<NS, NS, false>(a, I, J, 0, z, x, sm, tt, wl, wb, ef, s.epoch, iter == GS_ITMAX);
         __syncthreads();       // every thread's stores are issued; shared memory is free for the next tile
         if (threadIdx.x == 0) {
             __threadfence();
