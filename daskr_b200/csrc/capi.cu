@@ -338,7 +338,8 @@ void dkb_setup_rbdpre(const int *mx, const int *my, const int *ns, const int *ns
     c->jy0 = c->rank * base + std::min(c->rank, rem);
     c->npts = (i64)c->mx * c->my;
     c->halo = (i64)c->ns * c->mx;
-    c->halo_pad = ((c->halo + 31) / 32) * 32;
+    // several ranks: the Gauss-Seidel factor sweeps DKB_GS_OV_BELOW extra rows below (and fewer above) in place
+    c->halo_pad = ((c->halo * (c->nranks > 1 ? DKB_GS_OV_BELOW : 1) + 31) / 32) * 32;
     c->rbd_set = 1;
     c->rbg_set = 0;
     // blocks and pivots are device resident and sized in 64 bits: nothing is carved from rwork/iwork

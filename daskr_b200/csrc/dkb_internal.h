@@ -18,6 +18,8 @@ typedef int64_t i64;
 #define DKB_RED_BLOCK 512        // threads per block in reduction kernels
 #define DKB_RED_MAXGRID 1184     // 148 SMs x 8 resident blocks
 #define DKB_NSLOT 64             // device scalar slots
+#define DKB_GS_OV_BELOW 32        // gs.cu: rows of the slab below / above that a rank sweeps redundantly (see there)
+#define DKB_GS_OV_ABOVE 8
 
 enum { DKB_PROB_NONE = 0, DKB_PROB_WEB = 1, DKB_PROB_HEAT = 2 };
 
@@ -63,7 +65,7 @@ struct DkbCtx {
     int mx = 0, my_g = 0, my = 0, jy0 = 0, ns = 0, nsd = 0;
     i64 npts = 0;                // local mesh points
     i64 halo = 0;                // ns*mx doubles: one mesh row
-    i64 halo_pad = 0;            // halo rounded up to 32 doubles
+    i64 halo_pad = 0;            // room on both sides of every solver vector: one mesh row on one GPU, DKB_GS_OV_BELOW rows on several
 
     int problem = DKB_PROB_NONE;
     WebPar web;

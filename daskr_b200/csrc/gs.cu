@@ -405,8 +405,8 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 // solve couples a point to the rows below it through paths of weight beta^k*gamma^m with beta, gamma <= 1/4, which
 // sum to at most (1/3)^m over m rows -- 5e-16 at m = 32 -- and the U step reaches one row upwards per iteration,
 // four rows in all.  Own rows agree with the single-GPU sweep to rounding (not bit for bit).
-#define GS_OV_BELOW 32
-#define GS_OV_ABOVE 8
+#define GS_OV_BELOW DKB_GS_OV_BELOW
+#define GS_OV_ABOVE DKB_GS_OV_ABOVE
 static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x);
 
 int web_gauss_seidel(double hl0, double *z, double *x)
@@ -418,6 +418,14 @@ int web_gauss_seidel(double hl0, double *z, double *x)
     const int my_min = wp.my / c->nranks;                    // every slab has at least this many rows
     const int ob = std::min(GS_OV_BELOW, my_min), oa = std::min(GS_OV_ABOVE, my_min);
     const int nb = c->rank > 0 ? ob : 0, na = c->rank < c->nranks - 1 ? oa : 0;
+    const i64 n_own = (i64)c->my * mxns;
+    // The solver's vectors carry DKB_GS_OV_BELOW rows of room on both sides (alloc_solver): sweep in place, the overlap
+    // rows arrive straight in that room.  Any other caller's arrays go through a copy.
+    auto in_arena = [&](const double *p) { return c->arena && p >= c->arena && p < c->arena + c->arena_doubles; };
+    if (in_arena(z) && in_arena(x) && c->halo_pad >= (i64)ob * mxns) {
+        slab_overlap_exchange(z, n_own, (i64)ob * mxns, (i64)oa * mxns, z - (i64)nb * mxns, z + n_own);
+        return gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, z - (i64)nb * mxns, x - (i64)nb * mxns);
+    }
     const i64 need = (i64)(nb + c->my + na) * mxns;
     if (need > c->gs_cap) {
         cudaFree(c->gs_z);
@@ -429,13 +437,11 @@ int web_gauss_seidel(double hl0, double *z, double *x)
             return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the overlapped-slab work vectors");
         c->gs_cap = cap;
     }
-    const i64 n_own = (i64)c->my * mxns;
     double *zo = c->gs_z + (i64)nb * mxns;
     cudaMemcpyAsync(zo, z, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
     slab_overlap_exchange(z, n_own, (i64)ob * mxns, (i64)oa * mxns, c->gs_z, zo + n_own);
     const int rc = gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, c->gs_z, c->gs_x);
     cudaMemcpyAsync(z, zo, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
-    (void)x;
     return rc;
 }
 
