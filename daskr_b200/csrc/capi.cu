@@ -599,7 +599,7 @@ void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, doub
     *ierr = fetch_first_flag(c);
 }
 
-// psol, example/example_web.f90:346-391 with jpre = 1
+// psol, example/example_web.f90:346-391
 void dkb_web_psol(const int *neq, const double *t, const double *cc, const double *cdot, const double *savr,
                   double *wk, const double *cj, const double *wght, double *rwp, int *iwp, double *b,
                   const double *epslin, int *ierr, double *rpar, int *ipar)

@@ -48,7 +48,7 @@ enum {
 /* options for dkb_set_option */
 enum {
     DKB_OPT_DEVICE_IO = 1,  /* 1: y/yprime passed to dkb_daskr are device pointers */
-    DKB_OPT_FUSED = 2,      /* 1 (default): use the fused datv kernels for built-in problems */
+    DKB_OPT_FUSED = 2,      /* built-in problems: 2 (default) single-kernel datv, 1 two kernels, 0 plain callbacks */
     DKB_OPT_MAX_STEPS = 3   /* per-call step limit (reference: 500, src/daskr.f:2057) */
 };
 
@@ -110,8 +110,10 @@ void dkb_setup_rbgpre(const int *mx, const int *my, const int *ns, const int *ns
 int dkb_web_setpar(int np, int mx, int my);
 /* the same problem on [0,1] x [0,ay] (fields in y/ay, true spacing in the stencil); ay=1 is setpar */
 int dkb_web_setpar_ex(int np, int mx, int my, double ay);
-/* res / jac / psol of example_web.f90:190-224, 301-344, 346-391 (jpre=ipar(1) must
- * be 1, jbg=ipar(2) must be 0: reaction factor only, no grouping) */
+/* res / jac / psol of example_web.f90:190-224, 301-344, 346-391.  As in the example, ipar(1) = jpre selects the
+ * preconditioner -- 1: reaction factor A_R (rbdpre / rbgpre), 2: spatial Gauss-Seidel factor A_S, 3: A_S then A_R
+ * (the shipped setting), 4: A_R then A_S -- and ipar(2) = jbg selects block grouping (0: dkb_setup_rbdpre,
+ * 1: dkb_setup_rbgpre; must match the setup call that was made).  psol uses wk as N words of scratch. */
 void dkb_web_res(const double *t, const double *c, const double *cdot, const double *cj,
                  double *delta, int *ires, double *rpar, int *ipar);
 void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *c,
