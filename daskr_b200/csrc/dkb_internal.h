@@ -187,6 +187,7 @@ void v_gmres_dl(i64 n, int maxl, double *const *v, const double *q, double snorm
 void r_dot(i64 n, const double *x, const double *y, int slot);                 // ddot
 void r_sum_strided(i64 npts, i64 stride, i64 off, const double *x, int slot);  // sum_i x[i*stride+off] (root functions)
 void r_max(i64 n, const double *x, int slot);
+bool r_wrms3(i64 n, int nn, const double *e, const double *rwt, const double *phi_kp1, const double *phi_k, double *out);   // ddstp error estimates, one pass
 void r_cnstr(i64 n, const double *y, const double *ynew, const int *icnstr, int slot);   // dcnstr: [rdymx, hard flag]
 void v_cnst0(i64 n, const double *y, const int *icnstr, int *d_flag);                   // dcnst0: atomicMin(first bad index + 1)                                  // max_i x[i]
 void r_dot2(i64 n, const double *vnew, const double *v1, int slot);            // [vnew.vnew, v1.vnew]

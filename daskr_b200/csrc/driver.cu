@@ -352,6 +352,9 @@ static void k_ddstp(DkbCtx *c, double *t, const Cb &cb, double *h, int *jstart, 
                     double epscon, int *iphase, int *jcalc, int jflg, int *k, int *kold, int *ns, int nonneg,
                     int ntype)
 {
+    double nrm3[3];   // error estimates of BLOCK 4, one fused pass
+    int nnorm;
+    bool fused3;
     int *IWM = iwm - 1;
     const i64 neq = c->neq;
     double *alpha = alpha0_ - 1, *beta = beta0_ - 1, *gama = gama0_ - 1, *psi = psi0_ - 1, *sigma = sigma0_ - 1;
@@ -422,22 +425,26 @@ static void k_ddstp(DkbCtx *c, double *t, const Cb &cb, double *h, int *jstart, 
         if (iernls != 0) goto L600;
 
         // BLOCK 4: error estimates at orders k, k-1, k-2 (:360-378)
-        enorm = r_wrms(neq, c->e, c->vt);
+        // The three norms of this block in one pass over e, vt, phi(:,k+1), phi(:,k) (`delta` is scratch here in the
+        // reference and is not read again before the next Newton iteration overwrites it).
+        nnorm = (*k == 1) ? 1 : (*k == 2) ? 2 : 3;
+        fused3 = r_wrms3(neq, nnorm, c->e, c->vt, PHI_(kp1), PHI_(*k), nrm3);
+        enorm = fused3 ? nrm3[0] : r_wrms(neq, c->e, c->vt);
         erk = sigma[*k + 1] * enorm;
         terk = (*k + 1) * erk;
         est = erk;
         knew = *k;
 
         if (*k == 1) goto L430;
-        v_lin2(neq, 1.0, PHI_(kp1), 1.0, c->e, c->delta);
-        erkm1 = sigma[*k] * r_wrms(neq, c->delta, c->vt);
+        if (!fused3) v_lin2(neq, 1.0, PHI_(kp1), 1.0, c->e, c->delta);
+        erkm1 = sigma[*k] * (fused3 ? nrm3[1] : r_wrms(neq, c->delta, c->vt));
         terkm1 = (*k) * erkm1;
         if (*k > 2) goto L410;
         if (terkm1 <= terk / 2) goto L420;
         goto L430;
     L410:
-        v_lin2(neq, 1.0, c->delta, 1.0, PHI_(*k), c->delta);
-        erkm2 = sigma[*k - 1] * r_wrms(neq, c->delta, c->vt);
+        if (!fused3) v_lin2(neq, 1.0, c->delta, 1.0, PHI_(*k), c->delta);
+        erkm2 = sigma[*k - 1] * (fused3 ? nrm3[2] : r_wrms(neq, c->delta, c->vt));
         terkm2 = (*k - 1) * erkm2;
         if (std::max(terkm1, terkm2) > terk) goto L430;
     L420:

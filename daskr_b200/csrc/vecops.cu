@@ -559,6 +559,60 @@ double r_wrms(i64 n, const double *v, const double *rwt)
     return vmax * sqrt(r[0] / nn);
 }
 
+// ddstp's error estimates at orders k, k-1, k-2 (src/daskr_new.f90:360-378) in ONE pass: the weighted RMS norms of
+//   e,   phi(:,k+1) + e,   phi(:,k) + (phi(:,k+1) + e)
+// -- the reference forms the two sums in `delta` and takes three norms, 96 bytes per unknown; here 32.  nn = 1, 2, 3
+// norms (k = 1 needs only the first, k = 2 the first two).  Returns false if a plain sum of squares over/underflowed:
+// the caller then takes the reference's statement-by-statement route with the max-scaled norm.
+struct RWrms3 {
+    const double *e, *rwt, *p1, *p0;
+    int nn;
+    __device__ void init() {}
+    __device__ void operator()(i64 i, double (&a)[6]) const
+    {
+        const double w = rwt[i], ei = e[i];
+        double q = ei * w;
+        a[0] = a[0] + q * q;
+        a[3] = fmax(a[3], fabs(q));
+        if (nn > 1) {
+            const double d1 = p1[i] + ei;          // delta = phi(:,kp1) + e (:367)
+            q = d1 * w;
+            a[1] = a[1] + q * q;
+            a[4] = fmax(a[4], fabs(q));
+            if (nn > 2) {
+                const double d2 = p0[i] + d1;      // delta = phi(:,k) + delta (:374)
+                q = d2 * w;
+                a[2] = a[2] + q * q;
+                a[5] = fmax(a[5], fabs(q));
+            }
+        }
+    }
+};
+bool r_wrms3(i64 n, int nn, const double *e, const double *rwt, const double *phi_kp1, const double *phi_k, double *out)
+{
+    DkbCtx *c = g_ctx;
+    ProfScope ps(PROF_NORM);
+    const int slot = 52;
+    launch_reduce<3, 3>(RWrms3{e, rwt, phi_kp1, phi_k, nn}, n, slot);
+    allreduce_sum(slot, 3);
+    allreduce_max(slot + 3, 3);
+    double r[6];
+    scal_fetch(slot, 6, r);
+    const double cnt = (double)c->neq_g;
+    for (int k = 0; k < nn; ++k) {
+        const double sum = r[k], vmax = r[3 + k];
+        if (!(vmax > 0.0)) {
+            if (vmax == vmax) out[k] = 0.0;        // zero vector
+            else return false;                     // NaN: let the reference path report it
+        } else if (isfinite(sum) && sum > 1e-280) {
+            out[k] = sqrt(sum / cnt);
+        } else {
+            return false;
+        }
+    }
+    return true;
+}
+
 double r_nrm2(i64 n, const double *x)
 {
     double r;
