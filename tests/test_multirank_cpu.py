@@ -116,3 +116,90 @@ def test_slab_residual_and_norms_gloo(world):
     for rank, ok_res, ok_norm, _, _ in res:
         assert ok_res, "slab residual of rank %d differs from the full-mesh residual" % rank
         assert ok_norm, "all-reduced WRMS norm of rank %d differs" % rank
+
+
+# ---------------------------------------------------------------- Gauss-Seidel factor across slabs
+def _gs_sweeps(mat, rhs):
+    """5 lexicographic Gauss-Seidel iterations from x = 0 on mat x = rhs (what gauss_seidel computes,
+    tests/test_oracle_cpu.py::test_gauss_seidel_matches_the_residual_operator)."""
+    from scipy.linalg import solve_triangular
+
+    dl = np.tril(mat)
+    u = dl - mat
+    x = np.zeros(rhs.size)
+    for _ in range(5):
+        x = solve_triangular(dl, u @ x + rhs, lower=True)
+    return x
+
+
+def _gs_worker(rank, world, port, q):
+    """The multi-GPU form of the spatial factor with gloo standing in for NCCL: every rank sends its top
+    GS_OV_BELOW rows up and its bottom GS_OV_ABOVE rows down (slab_overlap_exchange, csrc/capi.cu), sweeps
+    [rows from below | own rows | rows from above] with the couplings across the window's ends dropped, keeps its
+    own rows.  Checker: the global sweep on the full mesh."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from daskr_b200.slab import partition, gs_overlap
+    from tests import oracle_py
+
+    orc = oracle_py.load()
+    np_, mx, my = 1, 12, 40 * world            # (anisotropic cells: the weakest damping, see the assertion)
+    ns = 2 * np_
+    row = ns * mx
+    neq = row * my
+    orc.web_setup(np_, mx, my)
+
+    def diffusion(c):
+        delta, rpar = orc.web_res(c, np.zeros(neq))
+        return -delta - rpar
+
+    jd = np.stack([diffusion(e) for e in np.eye(neq)], axis=1)
+    a = np.eye(neq) - (1.0 / 50.0) * jd
+    b = np.random.default_rng(1).standard_normal(neq)
+    full = _gs_sweeps(a, b)
+
+    jy0, myloc = partition(my, world, rank)
+    nb, na = gs_overlap(my, world, rank)
+    own = b[jy0 * row:(jy0 + myloc) * row].copy()
+    ob, oa = gs_overlap(my, world, 1)[0], gs_overlap(my, world, 0)[1]      # what neighbours expect from me
+    below = torch.empty(nb * row, dtype=torch.float64)
+    above = torch.empty(na * row, dtype=torch.float64)
+    reqs = []
+    if rank > 0:
+        reqs.append(dist.isend(torch.from_numpy(own[:oa * row].copy()), rank - 1))       # my bottom rows go down
+        reqs.append(dist.irecv(below, rank - 1))
+    if rank < world - 1:
+        reqs.append(dist.isend(torch.from_numpy(own[-ob * row:].copy()), rank + 1))      # my top rows go up
+        reqs.append(dist.irecv(above, rank + 1))
+    for r in reqs:
+        r.wait()
+    window_b = np.concatenate([below.numpy(), own, above.numpy()])
+    lo, hi = (jy0 - nb) * row, (jy0 + myloc + na) * row
+    ok_rows = np.array_equal(window_b, b[lo:hi])                      # the exchange delivered the right rows
+    win = _gs_sweeps(a[lo:hi, lo:hi], window_b)
+    got = win[nb * row: nb * row + myloc * row]
+    ref = full[jy0 * row:(jy0 + myloc) * row]
+    err = float(np.abs(got - ref).max() / np.abs(ref).max())
+    q.put((rank, bool(ok_rows), err))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_overlapped_slab_gauss_seidel_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 500) + world
+    procs = [ctx.Process(target=_gs_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_rows, err in res:
+        assert ok_rows, "rank %d received the wrong overlap rows" % rank
+        # anisotropic cells here (dy = dx*(mx-1)/(my-1)): the damping per row is between 1/3 and 1/2
+        assert err < 1e-7, "rank %d: own rows differ from the global sweep by %.2e" % (rank, err)
