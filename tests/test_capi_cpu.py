@@ -88,3 +88,48 @@ def test_slab_partition():
             for (a0, am), (b0, _) in zip(rows, rows[1:]):
                 assert a0 + am == b0
             assert max(m for _, m in rows) - min(m for _, m in rows) <= 1
+
+
+def test_block_grouping_tables_and_ownership():
+    """Host mirror of dkb_setup_rbgpre (daskr_b200/slab.py) against the oracle's set_grouping restatement, and the
+    multi-rank ownership of the group representatives: exactly one owner per group for every slab split."""
+    import ctypes as C
+
+    from daskr_b200.slab import partition, rbg_representatives, set_grouping
+    from tests import oracle_py
+
+    orc = oracle_py.load()
+    for mx, my, nxg, nyg in ((20, 20, 5, 5), (33, 27, 4, 3), (1024, 1024, 5, 5), (17, 90, 1, 7)):
+        jigx, jxr = set_grouping(mx, nxg)
+        jigy, jyr = set_grouping(my, nyg)
+        assert len(jigx) == mx and len(jigy) == my and min(jigx) == 1 and max(jigx) == nxg and max(jigy) == nyg
+        assert all(jigx[j - 1] == g + 1 for g, j in enumerate(jxr))      # a representative belongs to its own group
+        assert all(jigy[j - 1] == g + 1 for g, j in enumerate(jyr))
+        # the oracle (restating src/daskr_rbgpre.f90:160-193) solves every point with the block of group jig:
+        # with blocks = group number * identity, psol_rbgpre divides each point by its group number
+        ns = 2
+        orc.L.o_web_setpar(1, mx, my)
+        iw = np.zeros(64, dtype=np.int32)
+        orc.L.o_setup_rbgpre.argtypes = [C.c_int] * 7 + [C.c_void_p]
+        orc.L.o_setup_rbgpre(mx, my, ns, 1, nxg, nyg, 0, iw.ctypes.data_as(C.c_void_p))
+        ngrp = nxg * nyg
+        bd = np.concatenate([np.diag([g + 1.0] * ns).ravel() for g in range(ngrp)])
+        ip = np.tile(np.arange(1, ns + 1, dtype=np.int32), ngrp)
+        b = np.ones(ns * mx * my)
+        orc.L.o_psol_rbgpre.argtypes = [C.c_void_p] * 3
+        orc.L.o_psol_rbgpre(b.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), ip.ctypes.data_as(C.c_void_p))
+        grp = np.array([[(jigy[jy] - 1) * nxg + jigx[jx] for jx in range(mx)] for jy in range(my)], dtype=float)
+        assert np.allclose(b.reshape(my, mx, ns)[:, :, 0], 1.0 / grp)
+        for nranks in (1, 2, 3, 8):
+            if my < nranks:
+                continue
+            owners = np.zeros(ngrp, dtype=int)
+            for rank in range(nranks):
+                rep = rbg_representatives(mx, my, nxg, nyg, nranks, rank)
+                jy0, myloc = partition(my, nranks, rank)
+                for g, p in enumerate(rep):
+                    if p >= 0:
+                        owners[g] += 1
+                        jyl, jx = divmod(p, mx)
+                        assert jy0 + jyl + 1 == jyr[g // nxg] and jx + 1 == jxr[g % nxg]
+            assert (owners == 1).all()
