@@ -220,6 +220,8 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
     GS_CLK(4);
     // Persistent kernel: the right column and the top row are all that the neighbours of THIS sweep need.  Write them
     // first and flag them, so that the tiles to the right and above start their wavefront while phase C streams.
+    // (Phase C stores the same doubles to the same addresses once more; a reader that already holds the edge flag sees
+    // identical bits either way -- aligned 8-byte stores of equal values.)
     if (edge_flag) {
         for (int e = tid; e < hgt * SPC; e += blockDim.x) {
             const int r = e / SPC, ii = e - r * SPC;
