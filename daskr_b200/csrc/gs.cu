@@ -107,6 +107,10 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
             const bool has_up = jy0 + hgt < my;
             const int nrows = hgt + (has_up ? 1 : 0);
             const double *src = x + col0;
+            // the column to the right of the tile: one value per thread (hgt*SPC <= blockDim), in flight with the rest
+            const bool has_hr = (jx0 + w < mx) && tid < hgt * SPC;
+            double hr = 0.0;
+            if (has_hr) hr = __ldcg(&x[(i64)(jy0 + q) * mxns + (i64)(jx0 + w) * NS + g0 + i]);
             constexpr int UL = 17;                                        // 33 rows = two rounds of loads in flight
             for (int r0 = 0; r0 < nrows; r0 += UL) {
                 double v1[UL];
@@ -116,11 +120,7 @@ __device__ __forceinline__ void gs_tile(const GsArgs &a, int I, int J, int g0, d
                 for (int u = 0; u < UL; ++u)
                     if (mine && r0 + u < nrows) smp[(r0 + u) * PITCH] = v1[u];
             }
-            if (jx0 + w < mx)
-                for (int e = tid; e < hgt * SPC; e += blockDim.x) {
-                    const int rr = e / SPC, ii = e - rr * SPC;
-                    sm[(rr + 1) * PITCH + (w + 1) * SPC + ii] = __ldcg(&x[(i64)(jy0 + rr) * mxns + (i64)(jx0 + w) * NS + g0 + ii]);
-                }
+            if (has_hr) sm[(q + 1) * PITCH + (w + 1) * SPC + i] = hr;
             __syncthreads();
             for (int r0 = 0; r0 < hgt; r0 += UA) {
                 double v1[UA], v2[UA];
