@@ -141,11 +141,33 @@ def cpu_sample(steps, warmup, mesh=None):
     }
 
 
+def cpu_sample_native(steps, warmup, mesh=None):
+    """Courtesy number: the same oracle sources rebuilt on THIS host with -O3 -march=native
+    (FMA contraction allowed, so not the parity arithmetic) and timed on the same sample in a child process."""
+    import tempfile
+
+    odir = os.path.join(ROOT, "oracle")
+    srcs = [os.path.join(odir, f) for f in ("blas_linpack.cpp", "krylov.cpp", "rbdpre_problems.cpp", "daskr_driver.cpp")]
+    with tempfile.TemporaryDirectory() as tmp:
+        lib = os.path.join(tmp, "liboracle.so")
+        subprocess.run(["g++", "-O3", "-march=native", "-fPIC", "-std=c++17", "-shared", "-o", lib] + srcs + ["-lm"], check=True)
+        code = ("import sys, json; sys.path.insert(0, %r); import bench; from tests import oracle_py; oracle_py.LIB = %r; "
+                "oracle_py.ORACLE_DIR = %r; r = bench.cpu_sample(%d, %d, %r); print(json.dumps({k: r[k] for k in ('value', 'nli', 'wall_s')}))"
+                % (ROOT, lib, tmp, steps, warmup, mesh))
+        out = subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.PIPE, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     cb = cpu_sample(args.steps, args.warmup)
+    if args.cpu_native:
+        try:
+            cb["sample"] += "; courtesy rebuild with -O3 -march=native on this host: %.3f it/s" % cpu_sample_native(args.steps, args.warmup)["value"]
+        except Exception as ex:
+            cb["sample"] += "; courtesy -O3 -march=native run failed: %r" % (ex,)
     line = {
         "impl": "reference", "metric": "gmres_iters_per_s", "value": cb["value"], "unit": "it/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -461,6 +483,8 @@ def main():
                          "into slabs, e.g. --mx 4096 --my-per-gpu 512 --ay 1 at N=8 is BASELINE configs[3])")
     ap.add_argument("--jpre", type=int, default=1, help="food-web preconditioner: 1 = drbdpre (configs[1]); 3 = as shipped")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-native", action="store_true",
+                    help="--impl reference only: also time a -O3 -march=native rebuild of the oracle (courtesy number)")
     ap.add_argument("--cpu-mesh", type=int, default=None)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
