@@ -16,8 +16,9 @@
  * rbgpre), LINPACK, the food-web / heat routines and the Gauss-Seidel factor: the reference's tests never
  * exercise them and ship no expected outputs.  Those parts follow the reference source
  * line by line (citations are into /root/reference) and are cross-checked against independent facts only:
- * LAPACK pivots (scipy dgetrf), scipy's BLAS, the analytic heat-equation decay rate and self-consistency
- * between preconditioner variants.
+ * LAPACK pivots (scipy dgetrf), scipy's BLAS, numpy re-derivations of the food-web equations, of the analytic
+ * block Jacobian and of the Gauss-Seidel iteration, a nonsymmetric linear system solved by dslvk, the analytic
+ * heat-equation decay rate and self-consistency between preconditioner variants (tests/test_oracle_cpu.py).
  *
  * Arithmetic contract: the reference builds with gfortran for baseline x86-64,
  * i.e. separate multiply and add (no FMA contraction).  Build this with
