@@ -43,6 +43,7 @@ from .api import (  # noqa: F401
     prof_reset,
     prof_get,
     launch_count,
+    krylov_stats,
     comm_init_from_torch,
     OPT_DEVICE_IO,
     OPT_FUSED,

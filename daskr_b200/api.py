@@ -35,7 +35,7 @@ EXPORTS = [
     "dkb_state_bytes", "dkb_state_export", "dkb_state_import", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
-    "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count",
+    "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count", "dkb_krylov_stats", "dkb_reorth_stats", "dkb_alloc_workspace",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.dkb_rbd_leniwp.restype = C.c_int64
     L.dkb_rbd_to_reference.argtypes = [C.c_void_p] * 4
     L.dkb_rbd_from_reference.argtypes = [C.c_void_p] * 4
+    L.dkb_alloc_workspace.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64]
     L.dkb_daskr.restype = None
     L.dkb_daskr.argtypes = [C.c_void_p] * 21
     _lib = L
@@ -336,6 +337,13 @@ def prof_get():
 
 def launch_count():
     return int(lib().dkb_launch_count())
+
+
+def krylov_stats(n=16):
+    """Krylov iterations since prof_reset() by basis index ll = 1..n."""
+    h = np.zeros(n, dtype=np.int64)
+    _check(lib().dkb_krylov_stats(_p(h), n), "dkb_krylov_stats")
+    return h
 
 
 # ---------------------------------------------------------------- whole-run drivers

@@ -150,7 +150,7 @@ void halo_exchange3(double *a, double *b, double *cc)
 }
 
 // ---------------------------------------------------------------- profiling
-static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo", "tpp_psol_kernel", "resdatv_kernel", "datv_single_kernel"};
+static const char *prof_names[PROF_NSLOTS] = {"datv", "mgs", "psol0", "jac", "res", "vec", "norm", "halo", "tpp_psol_kernel", "resdatv_kernel", "datv_single_kernel", "krylov_iter", "gauss_seidel"};
 void prof_begin(int slot)
 {
     DkbCtx *c = g_ctx;
@@ -215,6 +215,7 @@ int dkb_init(int device)
     DkbCtx *c = new DkbCtx();
     c->device = device;
     g_ctx = c;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->nsm, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c->d_scal, sizeof(double) * DKB_NSLOT));
     CUDA_TRY(cudaMemset(c->d_scal, 0, sizeof(double) * DKB_NSLOT));
@@ -623,7 +624,7 @@ void dkb_web_psol(const int *neq, const double *t, const double *cc, const doubl
     // rwp / iwp hold the blocks in the interleaved layout dkb_web_jac wrote (psol_tpp.cu)
     if (jpre != 2) {
         if (jbg == 1) rbg_psol(rwp, iwp, b);   // psol_rbgpre
-        else tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1);
+        else if (tpp_psol(rwp, iwp, g_ctx->ns, g_ctx->npts, b, nullptr, nullptr, 1.0, b, -1) != 0) { *ierr = -1; return; }
     }
     if (jpre == 4) {
         if (web_gauss_seidel(hl0, b, wk) != 0) { *ierr = -1; return; }
@@ -926,6 +927,23 @@ int dkb_prof_reset(void)
         g_ctx->prof[i].launches = 0;
     }
     g_ctx->launches = 0;
+    for (int i = 0; i <= DKB_MAXL_MAX; ++i) g_ctx->ll_hist[i] = 0;
+    return 0;
+}
+// Krylov iterations since the last dkb_prof_reset, by basis index: hist[ll-1] = iterations of dspigm's loop taken at
+// index ll (1..n).  bench.py sums SURVEY 8(d)'s B_it(ll) over it.
+// dorth's conditional reorthogonalisation (src/daskr_new.f90:3575-3588): times the branch was entered / corrections applied
+int dkb_reorth_stats(int64_t *entered, int64_t *corrections)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    *entered = g_ctx->reorth_entered;
+    *corrections = g_ctx->reorth_corrections;
+    return 0;
+}
+int dkb_krylov_stats(int64_t *hist, int n)
+{
+    if (!g_ctx) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    for (int i = 0; i < n; ++i) hist[i] = (i + 1 <= DKB_MAXL_MAX) ? g_ctx->ll_hist[i + 1] : 0;
     return 0;
 }
 int dkb_prof_get(char *names, double *ms, int64_t *launches, int max_entries)

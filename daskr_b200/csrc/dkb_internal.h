@@ -42,12 +42,13 @@ struct ProfSlot {
     double ms;
     i64 launches;
 };
-enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV, PROF_DATV1,
+enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV, PROF_DATV1, PROF_KIT, PROF_GS,
        PROF_NSLOTS };
 
 // ---------------------------------------------------------------- context
 struct DkbCtx {
     int device = 0;
+    int nsm = 148;               // multiprocessor count of the device (launch-grid sizing)
     cudaStream_t stream = nullptr;
     char err[512] = {0};
     // options
@@ -122,6 +123,8 @@ struct DkbCtx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_slot;    // slot of pair i (events 2i, 2i+1)
     i64 launches = 0;
+    i64 reorth_entered = 0, reorth_corrections = 0;   // dorth:3575-3588 branch counters (tests)
+    i64 ll_hist[DKB_MAXL_MAX + 1] = {0};   // Krylov iterations taken at basis index ll (bench.py: whole-iteration roofline)
 };
 
 extern DkbCtx *g_ctx;

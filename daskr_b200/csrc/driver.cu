@@ -81,7 +81,8 @@ static int alloc_solver(DkbCtx *c, i64 neq, int maxl, int kmp, int need_vt, int 
         // IC scratch overlays the start of WM (daskr.f:1842-1844)
         c->yic = c->v[0];
         c->ypic = c->v[1];
-        c->pwk = c->v[2 <= maxl ? 2 : maxl];
+        // three distinct vectors (daskr.f:1842-1844); with maxl = 1 the basis has only two, so pwk takes the datv scratch
+        c->pwk = (maxl >= 2) ? c->v[2] : c->z;
         c->neq = neq;
         c->maxl = maxl;
         c->kmp = kmp;
@@ -115,6 +116,31 @@ static int alloc_solver(DkbCtx *c, i64 neq, int maxl, int kmp, int need_vt, int 
             c->leniwp = leniwp;
         }
     }
+    return 0;
+}
+
+// The solver workspace without a dkb_daskr call: what a host that keeps DASKR's own driver (the Fortran ddstp / dnedk /
+// dnsk of the north star) allocates once before it calls dkb_dslvk and the vector-op layer.  lenwp / leniwp: extra
+// preconditioner storage in doubles / ints on top of what dkb_setup_rbdpre / rbgpre imply (iwork(27:28) of the reference).
+extern "C" int dkb_alloc_workspace(int64_t neq, int maxl, int kmp, int64_t lenwp, int64_t leniwp)
+{
+    DkbCtx *c = g_ctx;
+    if (!c) return dkb_fail(DKB_E_STATE, "dkb_init not called");
+    if (neq <= 0 || maxl < 1 || maxl > DKB_MAXL_MAX || kmp < 1 || kmp > maxl)
+        return dkb_fail(DKB_E_ARG, "dkb_alloc_workspace: need neq > 0, 1 <= kmp <= maxl <= %d", DKB_MAXL_MAX);
+    if (c->rbd_set && neq != (i64)c->ns * c->npts)
+        return dkb_fail(DKB_E_ARG, "dkb_alloc_workspace: neq does not match the setup_rbdpre slab (ns*mx*myloc)");
+    int r = alloc_solver(c, neq, maxl, kmp, 1, 1, 0, 0, lenwp, leniwp);
+    if (r != 0) return r;
+    c->neq_g = neq;
+    if (c->nranks > 1) {
+        double ng = (double)neq;
+        cudaMemcpyAsync(c->d_scal + 50, &ng, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        allreduce_sum(50, 1);
+        scal_fetch(50, 1, &ng);
+        c->neq_g = (i64)(ng + 0.5);
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1263,11 +1289,6 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
         }
         cudaMemcpyAsync(c->d_id, &IW[c->s_lid], sizeof(int) * neq, cudaMemcpyHostToDevice, c->stream);
     }
-    if (INFO[2] == 1) {
-        cudaMemcpyAsync(c->d_rtol, rtol, sizeof(double) * neq, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(c->d_atol, atol, sizeof(double) * neq, cudaMemcpyHostToDevice, c->stream);
-    }
-
     if (tout == *t) { why = "tout == t"; goto L701; }
     if (INFO[7] != 0 && RW[LHMAX] <= 0.0) { why = "hmax <= 0"; goto L701; }
 
@@ -1328,6 +1349,17 @@ L200:
         if (INFO[2] == 0) break;
     }
     if (nzflg == 0) { why = "rtol = atol = 0"; goto L701; }
+    // The reference reads RTOL / ATOL in DDAWTS at every step and aliases VT to WT through the work-array pointers
+    // (daskr.f:1416-1427, LVT = LWT when info(16) = 0): both must hold on every call, whatever path set the state up
+    // (initial call, continuation, dkb_state_import).
+    if (INFO[2] == 1) {
+        if (!c->d_rtol && (cudaMalloc(&c->d_rtol, sizeof(double) * neq) != cudaSuccess ||
+                           cudaMalloc(&c->d_atol, sizeof(double) * neq) != cudaSuccess)) { why = "cannot allocate the tolerance vectors"; goto L701; }
+        cudaMemcpyAsync(c->d_rtol, rtol, sizeof(double) * neq, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(c->d_atol, atol, sizeof(double) * neq, cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);   // rtol / atol are the caller's pageable arrays
+    }
+    if (INFO[16] == 0) c->vt = c->wt;
     IW[LLCIWP] = 1;
     if (INFO[1] == 1) goto L400;
 
@@ -1336,7 +1368,6 @@ L200:
     *idid = 1;
     ier = ewt_set(c, tol, c->y, INFO[16] != 0);
     if (ier != 0) { why = "some element of wt is <= 0"; goto L701; }
-    if (INFO[16] == 0) c->vt = c->wt;
 
     uround = 2.220446049250313e-16;   // D1MACH(4), src/daux.f:2-11
     RW[LROUND] = uround;

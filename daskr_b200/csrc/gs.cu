@@ -453,6 +453,7 @@ int web_gauss_seidel(double hl0, double *z, double *x)
 static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x)
 {
     DkbCtx *c = g_ctx;
+    ProfScope ps(PROF_GS);
     const WebPar &wp = c->web;
     GsArgs a;
     a.mx = wp.mx;

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) heat_datv_kernel(HeatDev h, i64 n, const 
 static int hgrid(i64 n)
 {
     i64 g = (n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
+    if (g > g_ctx->nsm * 8) g = g_ctx->nsm * 8;
     if (g < 1) g = 1;
     return (int)g;
 }

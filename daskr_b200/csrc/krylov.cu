@@ -159,6 +159,7 @@ static double k_dorth(i64 n, double *vnew, double *const *v, double *hes, int ld
     // conditional reorthogonalisation (:3575-3588), evaluated in FP64 exactly as written
     volatile double probe = vnorm + snormw / 1000;
     if (probe != vnorm) return snormw;
+    g_ctx->reorth_entered += 1;
     double sumdsq = 0.0;
     for (int i = i0; i <= ll; ++i) {
         double d;
@@ -168,6 +169,7 @@ static double k_dorth(i64 n, double *vnew, double *const *v, double *hes, int ld
         volatile double probe2 = HES(i, ll) + tem / 1000;
         if (probe2 == HES(i, ll)) continue;
         HES(i, ll) = HES(i, ll) - tem;
+        g_ctx->reorth_corrections += 1;
         v_axpy(n, tem, v[i - 1], vnew);
         sumdsq = sumdsq + tem * tem;
     }
@@ -238,6 +240,8 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
     prod = 1.0;
     for (ll = 1; ll <= maxl; ++ll) {
         *lgmr = ll;
+        ProfScope kit(PROF_KIT);   // one Arnoldi iteration: datv + dorth (+ the normalisation of v(:,ll+1))
+        c->ll_hist[ll] += 1;
         k_datv(A, v[ll - 1], v[ll], ires, &ierr, nres, npsol);
         if (*ires < 0) {
             if (first) v_zero(neq, A.x);

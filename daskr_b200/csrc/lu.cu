@@ -247,7 +247,7 @@ static int lu_grid(i64 nblk, int G)
 {
     i64 gpb = 256 / G;
     i64 g = (nblk + gpb - 1) / gpb;
-    i64 cap = 148 * 8;
+    i64 cap = (i64)g_ctx->nsm * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -289,7 +289,7 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
     // measured (tools/bench_extra.py, 1e6 blocks): one thread per block wins for ns <= 2 and ns >= 20,
     // one sub-warp group per block in between
     if (ns <= 2 || ns >= 20) {
-        const int grid = (int)std::min<i64>((nblk + 127) / 128, 148 * 16);
+        const int grid = (int)std::min<i64>((nblk + 127) / 128, g_ctx->nsm * 16);
 #define CALL(N) dgesl_tpp_ref_kernel<N><<<grid, 128, 0, st>>>(bd, ipbd, nblk, b)
         NS_DISPATCH(ns, CALL)
 #undef CALL
@@ -314,7 +314,7 @@ int rbg_psol(const double *bd, const int *ipbd, double *b)
 {
     DkbCtx *c = g_ctx;
     const i64 npts = c->npts;
-    const int grid = (int)std::min<i64>((npts + 127) / 128, 148 * 16);
+    const int grid = (int)std::min<i64>((npts + 127) / 128, g_ctx->nsm * 16);
 #define CALL(N) rbg_psol_kernel<N><<<grid, 128, 0, c->stream>>>(bd, ipbd, c->d_jigx, c->d_jigy, c->mx, c->jy0, c->ngx, npts, b)
     NS_DISPATCH(c->ns, CALL)
 #undef CALL

@@ -205,7 +205,7 @@ int tpp_psol(const double *lut, const int *pt, int ns, i64 npts, const double *i
     DkbCtx *c = g_ctx;
     if (npts <= 0) return 0;
     i64 ntile = (npts + TPP_THREADS - 1) / TPP_THREADS;
-    int grid = (int)std::min<i64>(ntile, 148 * 4);
+    int grid = (int)std::min<i64>(ntile, g_ctx->nsm * 4);
     double *res = slot >= 0 ? c->d_scal + slot : nullptr;
     {
         ProfScope ps(PROF_TPP);   // events around this one launch: the roofline kernel of bench.py
@@ -227,7 +227,7 @@ int tpp_from_reference(int ns, i64 npts, const double *bd, const int *ipbd, doub
 {
     if (npts <= 0) return 0;
     i64 total = npts * ns * ns;
-    int grid = (int)std::min<i64>((total + 255) / 256, 148 * 8);
+    int grid = (int)std::min<i64>((total + 255) / 256, g_ctx->nsm * 8);
     tpp_relayout_kernel<0><<<grid, 256, 0, g_ctx->stream>>>(ns, npts, const_cast<double *>(bd), const_cast<int *>(ipbd), lut, pt);
     COUNT_LAUNCH();
     return 0;
@@ -236,7 +236,7 @@ int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double 
 {
     if (npts <= 0) return 0;
     i64 total = npts * ns * ns;
-    int grid = (int)std::min<i64>((total + 255) / 256, 148 * 8);
+    int grid = (int)std::min<i64>((total + 255) / 256, g_ctx->nsm * 8);
     tpp_relayout_kernel<1><<<grid, 256, 0, g_ctx->stream>>>(ns, npts, bd, ipbd, const_cast<double *>(lut), const_cast<int *>(pt));
     COUNT_LAUNCH();
     return 0;

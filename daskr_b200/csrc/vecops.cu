@@ -14,7 +14,7 @@
 static inline int map_grid(i64 n, int block)
 {
     i64 g = (n + block - 1) / block;
-    i64 cap = 148 * 8;
+    i64 cap = (i64)g_ctx->nsm * 8;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -22,7 +22,7 @@ static inline int map_grid(i64 n, int block)
 static inline int red_grid(i64 n)
 {
     i64 g = (n + DKB_RED_BLOCK * 4 - 1) / (DKB_RED_BLOCK * 4);
-    i64 cap = 148 * 4;   // 4 x 512 threads per SM = full occupancy
+    i64 cap = std::min<i64>((i64)g_ctx->nsm * 4, DKB_RED_MAXGRID);   // 4 x 512 threads per SM = full occupancy
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;

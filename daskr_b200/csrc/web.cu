@@ -282,7 +282,7 @@ static int grp_grid(i64 npts, int G, int block, int per_sm)
 {
     i64 gpb = block / G;
     i64 g = (npts + gpb - 1) / gpb;
-    i64 cap = 148 * (i64)per_sm;
+    i64 cap = g_ctx->nsm * (i64)per_sm;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;
@@ -435,6 +435,5 @@ int web_datv_fused(const double *v, const double *wt, double wscale, const doubl
         }
     }
     if (jpre != 1 && web_gauss_seidel(1.0 / cj, vtemp, x->wk) != 0) return -1;
-    tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1);
-    return 0;
+    return tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1) != 0 ? -1 : 0;
 }

@@ -164,6 +164,10 @@ int dkb_state_export(void *host_buf, int64_t nbytes);
 int dkb_state_import(const void *host_buf, int64_t nbytes);
 
 /* ---- the hot path as separate calls (what a Fortran dnsk/dnedk would bind) ---- */
+/* The device workspace dkb_daskr allocates on its initial call (solver vectors, Krylov basis v(:,1:maxl+1), WP/IWP),
+ * for hosts that keep DASKR's own driver and call dkb_dslvk / the vector-op layer directly: the part of
+ * rwork(LWM:) / iwork(LIWM:) that src/daskr.f:1560-1604 carves for the Krylov option.  Call after dkb_setup_rbdpre. */
+int dkb_alloc_workspace(int64_t neq, int maxl, int kmp, int64_t lenwp, int64_t leniwp);
 /* dslvk, src/daskr_new.f90:3036-3165.  Device arrays y, ydot, savr, x, ewt of
  * length neq; counters are accumulated into iwm(12,16,20,21) like the reference. */
 void dkb_dslvk(const int *neq, const double *y, const double *t, const double *ydot,
@@ -207,6 +211,10 @@ int dkb_prof_reset(void);
 /* name[i] (up to 32 entries of 48 chars), accumulated ms, launch counts */
 int dkb_prof_get(char *names, double *ms, int64_t *launches, int max_entries);
 int64_t dkb_launch_count(void);
+/* Krylov iterations since dkb_prof_reset by basis index: hist[ll-1], ll = 1..n (dspigm's loop, src/daskr_new.f90:3304-3361) */
+int dkb_krylov_stats(int64_t *hist, int n);
+/* dorth's conditional reorthogonalisation (src/daskr_new.f90:3575-3588): branch entered / corrections applied so far */
+int dkb_reorth_stats(int64_t *entered, int64_t *corrections);
 
 #ifdef __cplusplus
 }

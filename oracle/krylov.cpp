@@ -153,6 +153,13 @@ void o_dhels(const double *a, int lda, int n, const double *q, double *b)
 #define V(j) (v + ((long)(j) - 1) * n)
 
 /* src/daskr_new.f90:3522-3590 */
+static long g_reorth[2] = {0, 0}; /* test instrumentation: reorthogonalisation branch entered / corrections applied */
+void o_reorth_stats(long *out)
+{
+    out[0] = g_reorth[0];
+    out[1] = g_reorth[1];
+}
+
 void o_dorth(double *vnew, const double *v, double *hes, long n, int ll,
              int ldhes, int kmp, double *snormw)
 {
@@ -167,6 +174,7 @@ void o_dorth(double *vnew, const double *v, double *hes, long n, int ll,
     /* absorption test evaluated in FP64 exactly as written (:3575) */
     volatile double probe = vnorm + *snormw / 1000;
     if (probe != vnorm) return;
+    g_reorth[0] += 1;
 
     double sumdsq = 0.0;
     for (int i = i0; i <= ll; ++i) {
@@ -174,6 +182,7 @@ void o_dorth(double *vnew, const double *v, double *hes, long n, int ll,
         volatile double probe2 = HES(i, ll) + tem / 1000;
         if (probe2 == HES(i, ll)) continue;
         HES(i, ll) = HES(i, ll) - tem;
+        g_reorth[1] += 1;
         o_daxpy(n, tem, V(i), vnew);
         sumdsq = sumdsq + tem * tem;
     }

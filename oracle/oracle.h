@@ -119,6 +119,7 @@ void o_daskr(o_res_t res, const int *neq, double *t, double *y, double *yprime,
 
 /* ---- food-web problem, example/example_web.f90 ---- */
 void o_web_setpar(int np, int mx, int my);
+void o_web_window(int my_window, int jy_off); /* test sampling aid, see rbdpre_problems.cpp */
 void o_web_cinit(double *c, double *cdot, double pred_ic, double *rpar);
 void o_web_res(const double *t, const double *c, const double *cdot,
                const double *cj, double *delta, int *ires, double *rpar, int *ipar);

@@ -221,6 +221,7 @@ static int w_np, w_ns, w_mx, w_my, w_mxns;
 static double w_aa, w_ee, w_gg, w_bb, w_dprey, w_dpred, w_alpha, w_beta, w_ax, w_ay, w_dx, w_dy;
 static std::vector<double> w_acoef, w_bcoef, w_cox, w_coy, w_diff;
 static double w_pi;
+static int w_jyoff = 0; /* o_web_window: global row of window row 1 minus 1 (0 for the whole mesh) */
 #define ACOEF(i, j) w_acoef[((j) - 1) * w_ns + ((i) - 1)]
 
 /* example/example_web.f90:19-58, with np / mx / my as run-time values
@@ -231,6 +232,7 @@ void o_web_setpar(int np, int mx, int my)
     w_ns = 2 * np;
     w_mx = mx;
     w_my = my;
+    w_jyoff = 0;
     w_mxns = mx * w_ns;
     w_pi = 4 * std::atan(1.0);
     w_acoef.assign((size_t)w_ns * w_ns, 0.0);
@@ -271,12 +273,23 @@ void o_web_setpar(int np, int mx, int my)
     }
 }
 
+/* Test sampling aid (not in the reference): after o_web_setpar(np, mx, my_global), restrict the row loops of
+ * f / res / cinit to a window of `my_window` rows whose first row is global row jy_off + 1.  Mesh spacing and
+ * coefficients stay those of the whole mesh; the window's first and last rows see mirrored neighbours (wrong unless
+ * they are the global boundary), so callers compare interior window rows only.  Lets the full-size GPU kernels be
+ * checked against the restated arithmetic on a few rows of a 4096 x 4096 mesh. */
+void o_web_window(int my_window, int jy_off)
+{
+    w_my = my_window;
+    w_jyoff = jy_off;
+}
+
 /* example/example_web.f90:271-299 */
 void o_web_rates(const double *t, const int *jx, const int *jy, const double *c, double *rxy)
 {
     (void)t;
     const int ns = w_ns;
-    double y = (*jy - 1) * w_dy;
+    double y = (*jy - 1 + w_jyoff) * w_dy;
     double x = (*jx - 1) * w_dx;
     double fac = 1.0 + w_alpha * x * y + w_beta * std::sin(4 * w_pi * x) * std::sin(4 * w_pi * y);
 
