@@ -251,6 +251,8 @@ int dkb_finalize(void)
     cudaFree(c->gs_ticket);
     cudaFree(c->gs_done);
     cudaFree(c->gs_first);
+    cudaFree(c->gss_hbuf);
+    cudaFree(c->gss_ticket);
     cudaFree(c->d_jigx);
     cudaFree(c->d_jigy);
     cudaFree(c->d_rep);

@@ -106,6 +106,9 @@ struct DkbCtx {
     int gs_ntx = 0, gs_nty = 0, gs_nt = 0, gs_total = 0;
     double *gs_z = nullptr, *gs_x = nullptr;   // gs.cu: overlapped-slab work vectors (several ranks only)
     i64 gs_cap = 0;
+    size_t gss_hwords = 0;                               // gs_stream.cu
+    double *gss_hbuf = nullptr;                          // strip exchange buffer (all words GSS_EMPTY between applications)
+    unsigned *gss_ticket = nullptr;
     double *d_scal = nullptr;    // DKB_NSLOT doubles
     double *h_scal = nullptr;    // pinned
     double *d_part = nullptr;    // DKB_RED_MAXGRID * 8 partials
@@ -224,6 +227,7 @@ int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double 
 void web_upload_tables();
 void web_res_launch(const double *c, const double *cdot, double *delta);
 int web_gauss_seidel(double hl0, double *z, double *x);
+int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z);   // gs_stream.cu: the five sweeps in one pass
 // block-grouped reaction factor (jbg = 1): FD blocks at the representative points (unfactored, reference layout)
 void web_jac_groups_launch(const double *c, const double *rewt, double *bd);
 void rbg_add_cj(double *bd, int ns, int nsd, int ngrp, double cj);

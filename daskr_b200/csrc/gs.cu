@@ -454,6 +454,12 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
 {
     DkbCtx *c = g_ctx;
     ProfScope ps(PROF_GS);
+    // Default: all five iterations in one streaming pass (gs_stream.cu).  DKB_GS_STREAM=0 keeps the five-pass tile
+    // scheduler below (A/B runs, cross-check in the tests).
+    {
+        const char *st_env = getenv("DKB_GS_STREAM");
+        if (!(st_env && atoi(st_env) == 0)) return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z);
+    }
     const WebPar &wp = c->web;
     GsArgs a;
     a.mx = wp.mx;

@@ -1,0 +1,320 @@
+// gs_stream.cu -- the food-web example's spatial preconditioner factor (gauss_seidel,
+// example/example_web.f90:393-575) with ALL FIVE Gauss-Seidel iterations fused into one pass over the mesh.
+//
+// The reference runs itmax = 5 lexicographic iterations on A_S = I - hl0*J_d, species by species:
+//   (U)  x(p) := beta*x(p+1) + gamma*x(p+row)                     iterations 2..5; previous iterate (ahead in sweep order)
+//   (L)  x(p) := (x(p) + beta*x(p-1)) + gamma*x(p-row)            needs the NEW left / lower values
+//   (S)  z    := z + x
+// Iteration k at point (c,r) needs iteration k at (c-1,r), (c,r-1) and iteration k-1 at (c+1,r), (c,r+1): nothing
+// else.  gs.cu runs the five iterations as five passes (x and z read and written five times: 160 bytes per unknown).
+// Here each value is produced once and consumed from registers:
+//
+//   * a WARP owns one species on a strip of 32 mesh columns and streams up the rows; lane l works on column
+//     32*I - (k-1) + l in iteration k (the strip shifts one column to the left per iteration, so the right-hand
+//     neighbour of iteration k-1 is always in the same lane);
+//   * at step s lane l updates row s - l - (k-1) of iteration k, for all five k at once.  With that skew every
+//     operand is either the lane's own result of the previous step (lower neighbour; right neighbour of the previous
+//     iterate) or the result of lane l-1 of the previous step (left neighbour; upper neighbour of the previous
+//     iterate): one __shfl_up per iteration and step, five independent dependency chains per warp;
+//   * the running sum z = ((((0 + x1) + x2) + x3) + x4) + x5 follows the mesh point from lane to lane the same way
+//     (the point visited by lane l in iteration k is visited by lane l+1 in iteration k+1, two steps later);
+//   * lane 0's left-hand operands come from the strip to the left, which runs >= 48 steps ahead and leaves its lane-31
+//     results (5 iterates + 4 partial sums per row) in a global exchange buffer (L2 resident); a persistent CTA takes
+//     (strip, species group) items in strip order from a ticket counter, so a CTA only ever waits for a CTA that is
+//     already running (no deadlock for any number of resident CTAs);
+//   * z enters and leaves through a 64-row circular window in shared memory, loaded and stored in coalesced batches of
+//     8 rows by the whole CTA (SPC species of 32 points = whole 32-byte sectors), in place: a point's input slot is
+//     reused for its result.
+// Traffic: z read once and written once (16 bytes per unknown) + 2*10/32 words per unknown of strip exchange, instead
+// of 160.  Every point is updated by the reference's expression on the reference's operands in the reference's order,
+// so the result is bit-identical to the sequential sweeps (tests/test_gpu_gs.py).
+#include "dkb_internal.h"
+
+#define GSS_B 8        // steps (= rows entering the window) per batch
+#define GSS_WIN 64     // rows of the circular z window
+#define GSS_HS 10      // doubles per exchange slot: x1..x5, sum1..sum4, pad
+#define GSS_EMPTY (-1LL)   // bit pattern of an exchange word that has not been written: all ones (cudaMemset 0xFF), a NaN payload
+                           // that no floating-point instruction returns (results carry the canonical NaN)
+
+struct GssArgs {
+    int mx, H, nstrips, ng;      // H = rows swept
+    int bot_bnd, top_bnd;        // first / last row is a domain boundary (mirror coefficient gamma2 = 2*gamma1)
+    int s0_last;                 // first step of the last batch (the window is flushed by then)
+    i64 hp;                      // exchange slots per (strip boundary, species)
+    double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];
+};
+__device__ __forceinline__ double gss_poll(const double *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return __longlong_as_double((long long)v);
+}
+
+// One step of all five iterations for this lane.  FAST: every lane and iteration is on an interior point (no masks,
+// no boundary coefficients).  P[k]: this lane's result of iteration k+1 in the previous step; A1/A2[k]: partial sum
+// after iteration k+1, one / two steps ago.
+template <bool FAST, int SPC>
+__device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int colbase, double b1, double g1, double dinv,
+                                         double (&P)[5], double (&A1)[4], double (&A2)[4], double *zin_slot, double *zout_slot,
+                                         const double *hs /*this step's exchange slot (lane 0) or null*/,
+                                         double *hout_x /*lane 31: slot s-31*/, double *hout_a /*lane 31: slot s-30*/)
+{
+    const unsigned full = 0xffffffffu;
+    double S[5], T[4];
+    double OX[5], OA[4];   // what lane 31 hands to the next strip: never GSS_EMPTY (inactive points hand over 0)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) S[k] = __shfl_up_sync(full, P[k], 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) T[k] = __shfl_up_sync(full, A2[k], 1);
+    if (hs != nullptr) {   // lane 0 of a strip with a left neighbour
+#pragma unroll
+        for (int k = 0; k < 5; ++k) S[k] = hs[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) T[k] = hs[5 + k];
+    }
+    const double zin = *zin_slot;
+#pragma unroll
+    for (int k = 5; k >= 1; --k) {
+        const int r = s - lane - (k - 1);
+        const int ck = colbase - (k - 1);
+        const bool act = FAST || ((unsigned)r < (unsigned)a.H && (unsigned)ck < (unsigned)a.mx);
+        double rhs;
+        if (k == 1) {
+            rhs = dinv * zin;                                                  // x = dinv*z (:470-481)
+        } else {
+            const double xr = P[k - 2], xu = S[k - 2];                         // iterate k-1 at (c+1,r) and (c,r+1)
+            if (FAST) {
+                rhs = b1 * xr + g1 * xu;
+            } else {                                                           // (D-inverse)*U*x (:486-530)
+                const double betU = (ck == 0) ? 2 * b1 : b1;
+                const double gamU = (r == 0 && a.bot_bnd) ? 2 * g1 : g1;
+                const double t1 = betU * xr, t2 = gamU * xu;
+                const bool has_right = ck < a.mx - 1, lasty = (r == a.H - 1);
+                rhs = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
+            }
+        }
+        double v = rhs;                                                        // [(I - (D-inverse)*L)]-inverse (:532-566)
+        if (FAST) {
+            v = (v + b1 * S[k - 1]) + g1 * P[k - 1];
+        } else {
+            const double betL = (ck == a.mx - 1) ? 2 * b1 : b1;
+            const double gamL = (r == a.H - 1 && a.top_bnd) ? 2 * g1 : g1;
+            if (ck > 0) v = v + betL * S[k - 1];
+            if (r > 0) v = v + gamL * P[k - 1];
+        }
+        const double sum = (k == 1) ? 0.0 + v : T[k - 2] + v;                  // z := z + x (:568-570), z zeroed at :478
+        if (k == 5) {
+            if (act) *zout_slot = sum;
+        } else {
+            A2[k - 1] = A1[k - 1];
+            A1[k - 1] = sum;
+            OA[k - 1] = (FAST || act) ? sum : 0.0;
+        }
+        P[k - 1] = v;
+        OX[k - 1] = (FAST || act) ? v : 0.0;
+    }
+    if (hout_x != nullptr) {   // lane 31 of a strip with a right neighbour
+#pragma unroll
+        for (int k = 0; k < 5; ++k) __stcg(hout_x + k, OX[k]);
+    }
+    if (hout_a != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) __stcg(hout_a + 5 + k, OA[k]);
+    }
+}
+
+template <int NS, int SPC>
+__global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
+                                                            double *__restrict__ z, double *__restrict__ hbuf)
+{
+    constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);   // (PITCH - SPC) odd: the skewed accesses hit 32 different banks
+    constexpr int NHL = (GSS_B * GSS_HS + 31) / 32;              // exchange words per lane and batch
+    extern __shared__ double sm[];
+    double *zwin = sm;                                           // [GSS_WIN][PITCH]
+    double *hst = sm + GSS_WIN * PITCH;                          // [SPC][2][GSS_B*GSS_HS]
+    __shared__ int cur;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int pt = tid / SPC, si = tid - pt * SPC;               // load / store phases: point of the strip row, species of the group
+    const int mx = a.mx, H = a.H;
+    const i64 mxns = (i64)mx * NS;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) cur = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+        const int item = cur;
+        if (item >= total) return;
+        const int I = item / a.ng, g = item - I * a.ng, g0 = g * SPC;
+        const int sp = g0 + w;                                   // this warp's species
+        const double b1 = a.beta1[sp], g1 = a.gamma1[sp], dinv = a.dinv[sp];
+        const int colbase = 32 * I + lane;
+        const bool has_prod = I > 0, has_cons = I < a.nstrips - 1;
+        const int cl = 32 * I + pt, cs = 32 * I - 4 + pt;        // columns this thread loads / stores
+        const bool cl_ok = cl < mx, cs_ok = cs >= 0 && cs < mx;
+        const i64 offl = (i64)cl * NS + g0 + si, offs = (i64)cs * NS + g0 + si;
+        double *hprod = has_prod ? hbuf + ((i64)(I - 1) * NS + sp) * a.hp * GSS_HS : nullptr;
+        double *hcons = has_cons ? hbuf + ((i64)I * NS + sp) * a.hp * GSS_HS : nullptr;
+        double *hmine = hst + w * (2 * GSS_B * GSS_HS);
+        // interior strip: every column of every iteration has both neighbours
+        const bool strip_fast = (I >= 1) && (32 * I + 31 <= mx - 2);
+
+        double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
+        double zl[GSS_B], hl[NHL];
+
+        // ---- prologue: rows [0, GSS_B) of z and the exchange slots of steps [0, GSS_B) are fetched like every later
+        // batch's (registers now, shared memory at the end of the "batch" s0 = -GSS_B, which has no steps) ----
+        for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
+            const int rp = (s0 / GSS_B) & 1, wp = rp ^ 1;          // exchange staging buffers read by this batch / filled for the next
+            __syncthreads();
+            // ---- z rows [s0+8, s0+16) and the exchange slots of the next batch: loads in flight during the steps ----
+#pragma unroll
+            for (int j = 0; j < GSS_B; ++j) {
+                const int r = s0 + GSS_B + j;
+                const bool ok = cl_ok && r < H;
+                zl[j] = ok ? __ldcg(z + (i64)r * mxns + offl) : 0.0;
+            }
+            if (has_prod) {
+#pragma unroll
+                for (int m = 0; m < NHL; ++m) {
+                    const int idx = lane + 32 * m;
+                    hl[m] = (idx < GSS_B * GSS_HS) ? __ldcg(hprod + (i64)(s0 + GSS_B) * GSS_HS + idx) : 0.0;
+                }
+            }
+            // ---- finished rows [s0-44, s0-36) leave the window ----
+            if (cs_ok && s0 >= 37) {
+#pragma unroll
+                for (int j = 0; j < GSS_B; ++j) {
+                    const int r = s0 - 44 + j;
+                    if (r >= 0 && r < H) z[(i64)r * mxns + offs] = zwin[(r & (GSS_WIN - 1)) * PITCH + pt * SPC + si];
+                }
+            }
+            // ---- GSS_B steps ----
+            if (s0 >= 0 && s0 <= H + 35) {
+                const bool fast = strip_fast && (s0 - 35 >= 1) && (s0 + GSS_B - 1 <= H - 2);
+                const double *hsb = (has_prod && lane == 0) ? hmine + rp * (GSS_B * GSS_HS) : nullptr;
+                double *hcl = (has_cons && lane == 31) ? hcons : nullptr;
+                // (not unrolled beyond 2: eight inlined steps are ~28 KB of code per path and the warps of an SM sit at
+                // different places in it)
+                if (fast) {
+#pragma unroll 2
+                    for (int j = 0; j < GSS_B; ++j) {
+                        const int s = s0 + j;
+                        double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
+                        gss_step<true, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                            hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr, hcl ? hcl + (i64)(s - 30) * GSS_HS : nullptr);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < GSS_B; ++j) {
+                        const int s = s0 + j;
+                        double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
+                        // only the slots the right-hand strip waits for (steps it has an active lane 0 in) are written
+                        gss_step<false, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                             (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr,
+                                             (hcl && s >= 30 && s - 30 <= H + 3) ? hcl + (i64)(s - 30) * GSS_HS : nullptr);
+                    }
+                }
+            }
+            // ---- the prefetched rows / slots enter shared memory (read from the next batch on) ----
+#pragma unroll
+            for (int j = 0; j < GSS_B; ++j) {
+                const int r = s0 + GSS_B + j;
+                zwin[(r & (GSS_WIN - 1)) * PITCH + (pt + 4) * SPC + si] = zl[j];
+            }
+            if (has_prod) {
+                // Every exchange word is its own flag: the buffer holds GSS_EMPTY (a NaN no arithmetic produces) until the
+                // left strip's lane 31 stores the value (one aligned 8-byte store), and goes back to GSS_EMPTY as soon as it
+                // has been taken.  No fences, no progress counters: a word is either there or not.
+#pragma unroll
+                for (int m = 0; m < NHL; ++m) {
+                    const int idx = lane + 32 * m;
+                    const int slot = s0 + GSS_B + idx / GSS_HS, q = idx - (idx / GSS_HS) * GSS_HS;
+                    if (idx < GSS_B * GSS_HS && q < GSS_HS - 1 && slot <= H + 3) {
+                        double *src = hprod + (i64)(s0 + GSS_B) * GSS_HS + idx;
+                        while (__double_as_longlong(hl[m]) == GSS_EMPTY) {
+                            __nanosleep(20);
+                            hl[m] = gss_poll(src);
+                        }
+                        __stcg(src, __longlong_as_double(GSS_EMPTY));
+                        hmine[wp * (GSS_B * GSS_HS) + idx] = hl[m];
+                    }
+                }
+            }
+        }
+    }
+}
+
+static int gss_spc(int ns) { return ns % 4 == 0 ? 4 : ns % 5 == 0 ? 5 : ns % 3 == 0 ? 3 : ns % 2 == 0 ? 2 : 1; }
+
+template <int NS, int SPC>
+static int gss_launch(const GssArgs &a, unsigned *ticket, int total, double *z, double *hbuf)
+{
+    DkbCtx *c = g_ctx;
+    constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);
+    const size_t smem = sizeof(double) * ((size_t)GSS_WIN * PITCH + (size_t)SPC * 2 * GSS_B * GSS_HS);
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * SPC, smem);
+        per_sm = std::max(1, per_sm);
+    }
+    const int grid = std::min(total, c->nsm * per_sm);
+    gs_stream_kernel<NS, SPC><<<grid, 32 * SPC, smem, c->stream>>>(a, ticket, total, z, hbuf);
+    return 0;
+}
+
+// z := (approximately) A_S^-1 z over `my` rows, in place.  Same contract as gs_sweep() of gs.cu.
+int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z)
+{
+    DkbCtx *c = g_ctx;
+    const WebPar &wp = c->web;
+    const int ns = wp.ns;
+    GssArgs a;
+    a.mx = wp.mx;
+    a.H = my;
+    a.bot_bnd = bot_bnd;
+    a.top_bnd = top_bnd;
+    for (int i = 0; i < ns; ++i) {   // :447-457
+        const double elamda = 1.0 / (1.0 + 2 * hl0 * (wp.cox[i] + wp.coy[i]));
+        a.beta1[i] = hl0 * wp.cox[i] * elamda;
+        a.gamma1[i] = hl0 * wp.coy[i] * elamda;
+        a.dinv[i] = elamda;
+    }
+    const int spc = gss_spc(ns);
+    a.ng = ns / spc;
+    a.nstrips = (wp.mx + 4 + 31) / 32;      // iteration k covers columns shifted k-1 to the left: 4 more columns at the right end
+    a.hp = ((i64)(my + 64 + GSS_B - 1) / GSS_B) * GSS_B + 2 * GSS_B;
+    a.s0_last = ((my + 36 + GSS_B - 1) / GSS_B) * GSS_B;
+    const size_t hwords = (size_t)std::max(a.nstrips - 1, 1) * ns * a.hp * GSS_HS;
+    if (hwords > c->gss_hwords) {
+        cudaFree(c->gss_hbuf);
+        c->gss_hbuf = nullptr;
+        c->gss_hwords = 0;
+        if (cudaMalloc(&c->gss_hbuf, sizeof(double) * hwords) != cudaSuccess)
+            return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the strip exchange buffer (%zu MB)", hwords >> 17);
+        // every word GSS_EMPTY; the kernel leaves the buffer in that state (each word is taken exactly once)
+        cudaMemsetAsync(c->gss_hbuf, 0xFF, sizeof(double) * hwords, c->stream);
+        c->gss_hwords = hwords;
+    }
+    if (!c->gss_ticket && cudaMalloc(&c->gss_ticket, sizeof(unsigned)) != cudaSuccess)
+        return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the ticket counter");
+    cudaMemsetAsync(c->gss_ticket, 0, sizeof(unsigned), c->stream);
+    const int total = a.nstrips * a.ng;
+    int rc = 0;
+#define GSS_CASE(n, s) case n: rc = gss_launch<n, s>(a, c->gss_ticket, total, z, c->gss_hbuf); break;
+    switch (ns) {
+        GSS_CASE(1, 1) GSS_CASE(2, 2) GSS_CASE(3, 3) GSS_CASE(4, 4) GSS_CASE(5, 5) GSS_CASE(6, 3) GSS_CASE(7, 1) GSS_CASE(8, 4)
+        GSS_CASE(9, 3) GSS_CASE(10, 5) GSS_CASE(11, 1) GSS_CASE(12, 4) GSS_CASE(13, 1) GSS_CASE(14, 2) GSS_CASE(15, 5)
+        GSS_CASE(16, 4) GSS_CASE(17, 1) GSS_CASE(18, 3) GSS_CASE(19, 1) GSS_CASE(20, 4) GSS_CASE(21, 3) GSS_CASE(22, 2)
+        GSS_CASE(23, 1) GSS_CASE(24, 4) GSS_CASE(25, 5) GSS_CASE(26, 2) GSS_CASE(27, 3) GSS_CASE(28, 4) GSS_CASE(29, 1)
+        GSS_CASE(30, 5) GSS_CASE(31, 1) GSS_CASE(32, 4)
+    default: return dkb_fail(DKB_E_UNSUPPORTED, "Gauss-Seidel factor: ns=%d out of range 1..32", ns);
+    }
+#undef GSS_CASE
+    COUNT_LAUNCH();
+    dkb_cuda_check("gs_stream_sweep");
+    return rc;
+}

@@ -33,7 +33,11 @@ def _gpu_psol(dk, np_, mx, my, jpre, cj, b, lu=None):
 
 
 @pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (1, 33, 31), (2, 70, 45), (3, 32, 64), (10, 64, 40), (10, 100, 70),
-                                       (16, 40, 50)])
+                                       (16, 40, 50),
+                                       # strip edges of the streaming kernel: mx around multiples of 32 (the last strip holds
+                                       # only the columns the later iterations shifted out), very few / many rows, one column
+                                       (1, 28, 9), (1, 29, 9), (2, 31, 3), (2, 36, 2), (1, 60, 1), (5, 61, 140), (1, 1, 40),
+                                       (1, 2, 2), (4, 96, 33), (7, 65, 17), (10, 300, 50), (1, 128, 700)])
 @pytest.mark.parametrize("cj", [1e8, 2.5e3, 7.0])
 def test_gauss_seidel_bit_exact(dk, oracle, np_, mx, my, cj):
     ns = 2 * np_
@@ -47,9 +51,11 @@ def test_gauss_seidel_bit_exact(dk, oracle, np_, mx, my, cj):
 
 
 @pytest.mark.parametrize("env", [{"DKB_GS_TY": "32"}, {"DKB_GS_TY": "7"}, {"DKB_GS_PER_STEP": "1"},
-                                 {"DKB_GS_PER_STEP": "1", "DKB_GS_TY": "32"}])
+                                 {"DKB_GS_PER_STEP": "1", "DKB_GS_TY": "32"}, {}])
 def test_gauss_seidel_variants_bit_exact(dk, oracle, env, monkeypatch):
-    """The other tile heights and the one-launch-per-time-step schedule give the same bits."""
+    """The five-pass tile scheduler (DKB_GS_STREAM=0: the round-1 kernel, kept as a cross-check of the one-pass streaming
+    kernel) in its tile heights and launch schedules gives the same bits."""
+    monkeypatch.setenv("DKB_GS_STREAM", "0")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     for np_, mx, my in ((10, 100, 70), (2, 70, 45), (10, 64, 130)):

@@ -7,7 +7,7 @@ dk.init(0)
 L = dk.lib()
 import os
 M = int(os.environ.get('GS_MESH', '1024'))
-np_, mx, my = 10, M, M
+np_, mx, my = 10, M, int(os.environ.get('GS_ROWS', M))
 ns = 2 * np_
 iw = np.zeros(64, dtype=np.int32)
 dk.setup_rbdpre(mx, my, ns, np_, 0, iw)
