@@ -35,7 +35,9 @@ EXPORTS = [
     "dkb_state_bytes", "dkb_state_export", "dkb_state_import", "dkb_dslvk", "dkb_ddwnrm", "dkb_psol_rbdpre",
     "dkb_rbd_lenwp", "dkb_rbd_leniwp", "dkb_rbd_to_reference", "dkb_rbd_from_reference",
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
-    "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count", "dkb_krylov_stats", "dkb_reorth_stats", "dkb_alloc_workspace",
+    "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count", "dkb_krylov_stats", "dkb_reorth_stats", "dkb_alloc_workspace", "dkb_workspace_get",
+    "dkb_vcopy", "dkb_vscale", "dkb_vscale_to", "dkb_vaxpy", "dkb_lincomb", "dkb_ddot", "dkb_ewt_set_invert", "dkb_mask_vt",
+    "dkb_interp", "dkb_predict", "dkb_newton_update", "dkb_phi_update", "dkb_error_norms",
 ]
 
 
@@ -77,6 +79,21 @@ def lib():
     L.dkb_rbd_to_reference.argtypes = [C.c_void_p] * 4
     L.dkb_rbd_from_reference.argtypes = [C.c_void_p] * 4
     L.dkb_alloc_workspace.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64]
+    V, D, I64 = C.c_void_p, C.c_double, C.c_int64
+    L.dkb_workspace_get.argtypes = [C.c_int, V, V]
+    L.dkb_vcopy.argtypes = [I64, V, V]
+    L.dkb_vscale.argtypes = [I64, D, V]
+    L.dkb_vscale_to.argtypes = [I64, D, V, V]
+    L.dkb_vaxpy.argtypes = [I64, D, V, V]
+    L.dkb_lincomb.argtypes = [I64, D, V, D, V, V]
+    L.dkb_ddot.argtypes = [I64, V, V, V]
+    L.dkb_ewt_set_invert.argtypes = [I64, C.c_int, V, V, V, V, V, V, V]
+    L.dkb_mask_vt.argtypes = [I64, V, V, V]
+    L.dkb_interp.argtypes = [I64, D, D, C.c_int, V, I64, V, V, V]
+    L.dkb_predict.argtypes = [I64, C.c_int, V, I64, V, V, V]
+    L.dkb_newton_update.argtypes = [I64, V, D, V, V, V]
+    L.dkb_phi_update.argtypes = [I64, C.c_int, C.c_int, V, I64, V]
+    L.dkb_error_norms.argtypes = [I64, C.c_int, V, V, V, V, V]
     L.dkb_daskr.restype = None
     L.dkb_daskr.argtypes = [C.c_void_p] * 21
     _lib = L

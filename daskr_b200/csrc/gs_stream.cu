@@ -32,7 +32,18 @@
 
 #define GSS_B 8        // steps (= rows entering the window) per batch
 #define GSS_WIN 64     // rows of the circular z window
-#define GSS_HS 10      // doubles per exchange slot: x1..x5, sum1..sum4, pad
+#define GSS_HS 10      // doubles per exchange slot: x1..x5, sum1..sum4 of ONE step of the producer's lane 31, pad (80 bytes, 16-byte aligned)
+#ifdef GSS_DEBUG
+__device__ long long gss_dbg[4096 * 8];   // phase clocks of one CTA (the item in the middle of the schedule), per batch
+#define GSS_CLK(k) if (dbg && tid == 0) gss_dbg[dbgb * 8 + (k)] = clock64()
+#else
+#define GSS_CLK(k)
+#endif
+#ifdef GSS_WEAK_LD
+#define GSS_LDZ(p) (*(p))          // z is read once per application and was written by an earlier kernel: any cache will do
+#else
+#define GSS_LDZ(p) __ldcg(p)
+#endif
 #define GSS_EMPTY (-1LL)   // bit pattern of an exchange word that has not been written: all ones (cudaMemset 0xFF), a NaN payload
                            // that no floating-point instruction returns (results carry the canonical NaN)
 
@@ -56,8 +67,9 @@ __device__ __forceinline__ double gss_poll(const double *p)
 template <bool FAST, int SPC>
 __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int colbase, double b1, double g1, double dinv,
                                          double (&P)[5], double (&A1)[4], double (&A2)[4], double *zin_slot, double *zout_slot,
-                                         const double *hs /*this step's exchange slot (lane 0) or null*/,
-                                         double *hout_x /*lane 31: slot s-31*/, double *hout_a /*lane 31: slot s-30*/)
+                                         const double *hs_x /*lane 0: exchange slot of this step (x1..x5), or null*/,
+                                         const double *hs_a /*lane 0: slot of the previous step (sum1..sum4 at +5)*/,
+                                         double *hout /*lane 31: slot s-31, or null*/)
 {
     const unsigned full = 0xffffffffu;
     double S[5], T[4];
@@ -66,11 +78,11 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
     for (int k = 0; k < 5; ++k) S[k] = __shfl_up_sync(full, P[k], 1);
 #pragma unroll
     for (int k = 0; k < 4; ++k) T[k] = __shfl_up_sync(full, A2[k], 1);
-    if (hs != nullptr) {   // lane 0 of a strip with a left neighbour
+    if (hs_x != nullptr) {   // lane 0 of a strip with a left neighbour
 #pragma unroll
-        for (int k = 0; k < 5; ++k) S[k] = hs[k];
+        for (int k = 0; k < 5; ++k) S[k] = hs_x[k];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) T[k] = hs[5 + k];
+        for (int k = 0; k < 4; ++k) T[k] = hs_a[5 + k];
     }
     const double zin = *zin_slot;
 #pragma unroll
@@ -113,13 +125,13 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
         P[k - 1] = v;
         OX[k - 1] = (FAST || act) ? v : 0.0;
     }
-    if (hout_x != nullptr) {   // lane 31 of a strip with a right neighbour
-#pragma unroll
-        for (int k = 0; k < 5; ++k) __stcg(hout_x + k, OX[k]);
-    }
-    if (hout_a != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) __stcg(hout_a + 5 + k, OA[k]);
+    if (hout != nullptr) {   // lane 31 of a strip with a right neighbour: one 80-byte slot per step, five 16-byte stores
+        double2 *h2 = reinterpret_cast<double2 *>(hout);
+        __stcg(h2 + 0, make_double2(OX[0], OX[1]));
+        __stcg(h2 + 1, make_double2(OX[2], OX[3]));
+        __stcg(h2 + 2, make_double2(OX[4], OA[0]));
+        __stcg(h2 + 3, make_double2(OA[1], OA[2]));
+        __stcg(h2 + 4, make_double2(OA[3], 0.0));
     }
 }
 
@@ -160,19 +172,33 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 
         double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
         double zl[GSS_B], hl[NHL];
+#ifdef GSS_DEBUG
+        const bool dbg = (item == total / 2);
+#endif
 
         // ---- prologue: rows [0, GSS_B) of z and the exchange slots of steps [0, GSS_B) are fetched like every later
         // batch's (registers now, shared memory at the end of the "batch" s0 = -GSS_B, which has no steps) ----
         for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
             const int rp = (s0 / GSS_B) & 1, wp = rp ^ 1;          // exchange staging buffers read by this batch / filled for the next
+#ifdef GSS_DEBUG
+            const int dbgb = min((s0 + GSS_B) / GSS_B, 4095);
+#endif
+            GSS_CLK(0);
             __syncthreads();
+            GSS_CLK(1);
             // ---- z rows [s0+8, s0+16) and the exchange slots of the next batch: loads in flight during the steps ----
+            {
+                const int r0 = s0 + GSS_B;
+                const double *src = z + (i64)r0 * mxns + offl;
+                if (cl_ok && r0 + GSS_B <= H) {
 #pragma unroll
-            for (int j = 0; j < GSS_B; ++j) {
-                const int r = s0 + GSS_B + j;
-                const bool ok = cl_ok && r < H;
-                zl[j] = ok ? __ldcg(z + (i64)r * mxns + offl) : 0.0;
+                    for (int j = 0; j < GSS_B; ++j) zl[j] = GSS_LDZ(src + (i64)j * mxns);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < GSS_B; ++j) zl[j] = (cl_ok && r0 + j < H) ? GSS_LDZ(src + (i64)j * mxns) : 0.0;
+                }
             }
+            GSS_CLK(6);
             if (has_prod) {
 #pragma unroll
                 for (int m = 0; m < NHL; ++m) {
@@ -180,18 +206,34 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                     hl[m] = (idx < GSS_B * GSS_HS) ? __ldcg(hprod + (i64)(s0 + GSS_B) * GSS_HS + idx) : 0.0;
                 }
             }
+            GSS_CLK(7);
             // ---- finished rows [s0-44, s0-36) leave the window ----
+#ifndef GSS_NO_STORE
             if (cs_ok && s0 >= 37) {
+                const int r0 = s0 - 44;
+                double *dst = z + (i64)r0 * mxns + offs;
+                const double *wsrc = zwin + pt * SPC + si;
+                if (r0 >= 0 && r0 + GSS_B <= H) {
+                    double t[GSS_B];
 #pragma unroll
-                for (int j = 0; j < GSS_B; ++j) {
-                    const int r = s0 - 44 + j;
-                    if (r >= 0 && r < H) z[(i64)r * mxns + offs] = zwin[(r & (GSS_WIN - 1)) * PITCH + pt * SPC + si];
+                    for (int j = 0; j < GSS_B; ++j) t[j] = wsrc[((r0 + j) & (GSS_WIN - 1)) * PITCH];
+#pragma unroll
+                    for (int j = 0; j < GSS_B; ++j) dst[(i64)j * mxns] = t[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < GSS_B; ++j) {
+                        const int r = r0 + j;
+                        if (r >= 0 && r < H) dst[(i64)j * mxns] = wsrc[(r & (GSS_WIN - 1)) * PITCH];
+                    }
                 }
             }
+#endif
+            GSS_CLK(2);
             // ---- GSS_B steps ----
             if (s0 >= 0 && s0 <= H + 35) {
                 const bool fast = strip_fast && (s0 - 35 >= 1) && (s0 + GSS_B - 1 <= H - 2);
                 const double *hsb = (has_prod && lane == 0) ? hmine + rp * (GSS_B * GSS_HS) : nullptr;
+                const double *hsp = hmine + wp * (GSS_B * GSS_HS) + (GSS_B - 1) * GSS_HS;   // last slot of the previous batch
                 double *hcl = (has_cons && lane == 31) ? hcons : nullptr;
                 // (not unrolled beyond 2: eight inlined steps are ~28 KB of code per path and the warps of an SM sit at
                 // different places in it)
@@ -202,7 +244,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                         double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
                         double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
                         gss_step<true, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
-                                            hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr, hcl ? hcl + (i64)(s - 30) * GSS_HS : nullptr);
+                                            j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 } else {
 #pragma unroll 1
@@ -212,17 +254,19 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                         double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
                         // only the slots the right-hand strip waits for (steps it has an active lane 0 in) are written
                         gss_step<false, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
-                                             (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr,
-                                             (hcl && s >= 30 && s - 30 <= H + 3) ? hcl + (i64)(s - 30) * GSS_HS : nullptr);
+                                             j ? hsb + (j - 1) * GSS_HS : hsp,
+                                             (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 }
             }
+            GSS_CLK(3);
             // ---- the prefetched rows / slots enter shared memory (read from the next batch on) ----
 #pragma unroll
             for (int j = 0; j < GSS_B; ++j) {
                 const int r = s0 + GSS_B + j;
                 zwin[(r & (GSS_WIN - 1)) * PITCH + (pt + 4) * SPC + si] = zl[j];
             }
+            GSS_CLK(4);
             if (has_prod) {
                 // Every exchange word is its own flag: the buffer holds GSS_EMPTY (a NaN no arithmetic produces) until the
                 // left strip's lane 31 stores the value (one aligned 8-byte store), and goes back to GSS_EMPTY as soon as it
@@ -230,8 +274,8 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 #pragma unroll
                 for (int m = 0; m < NHL; ++m) {
                     const int idx = lane + 32 * m;
-                    const int slot = s0 + GSS_B + idx / GSS_HS, q = idx - (idx / GSS_HS) * GSS_HS;
-                    if (idx < GSS_B * GSS_HS && q < GSS_HS - 1 && slot <= H + 3) {
+                    const int slot = s0 + GSS_B + idx / GSS_HS;
+                    if (idx < GSS_B * GSS_HS && slot <= H + 3) {
                         double *src = hprod + (i64)(s0 + GSS_B) * GSS_HS + idx;
                         while (__double_as_longlong(hl[m]) == GSS_EMPTY) {
                             __nanosleep(20);
@@ -242,6 +286,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                     }
                 }
             }
+            GSS_CLK(5);
         }
     }
 }
@@ -318,3 +363,11 @@ int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z)
     dkb_cuda_check("gs_stream_sweep");
     return rc;
 }
+
+#ifdef GSS_DEBUG
+extern "C" void dkb_debug_gss_clocks(long long *out, int n)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, gss_dbg, sizeof(long long) * n);
+}
+#endif

@@ -21,6 +21,23 @@
         return 0;                                                                           \
     } while (0)
 
+struct FMaskVt {
+    const int *id;
+    const double *wt;
+    double *vt;
+    __device__ void operator()(i64 i) const
+    {
+        const int m = id[i] > 0 ? id[i] : 0;
+        vt[i] = (double)m * wt[i];
+    }
+};
+template <class F>
+__global__ void __launch_bounds__(256) vecapi_map_kernel(F f, i64 n)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+
 extern "C" {
 
 // dcopy (extern/dblas.f:48-95) as DASKR uses it: savr = delta (dnsk:2979), phi(:,1) = y (daskr.f:1918), r = x (dslvk:3121) ...
@@ -92,22 +109,6 @@ int dkb_ewt_set_invert(int64_t n, int iwt, const double *rtol, const double *ato
 }
 
 // vt = max(id, 0)*wt (src/daskr.f:1755, 1881, 2106-2109; info(16) = 1)
-struct FMaskVt {
-    const int *id;
-    const double *wt;
-    double *vt;
-    __device__ void operator()(i64 i) const
-    {
-        const int m = id[i] > 0 ? id[i] : 0;
-        vt[i] = (double)m * wt[i];
-    }
-};
-template <class F>
-__global__ void __launch_bounds__(256) vecapi_map_kernel(F f, i64 n)
-{
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
-}
 int dkb_mask_vt(int64_t n, const int *id, const double *wt, double *vt)
 {
     VEC_ENTER();

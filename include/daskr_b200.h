@@ -168,6 +168,36 @@ int dkb_state_import(const void *host_buf, int64_t nbytes);
  * for hosts that keep DASKR's own driver and call dkb_dslvk / the vector-op layer directly: the part of
  * rwork(LWM:) / iwork(LIWM:) that src/daskr.f:1560-1604 carves for the Krylov option.  Call after dkb_setup_rbdpre. */
 int dkb_alloc_workspace(int64_t neq, int maxl, int kmp, int64_t lenwp, int64_t leniwp);
+/* Device addresses of the workspace vectors (segments of rwork in the reference, src/daskr.f:1424-1427):
+ * which = 0 y, 1 yprime, 2 delta, 3 savr, 4 e, 5 wt, 6 vt, 7 phi(:,1), 8 v(:,1) (Krylov basis), 9 wp, 10 iwp;
+ * *ld = distance in doubles between consecutive columns of phi / v (0 for the others). */
+int dkb_workspace_get(int which, void **ptr, int64_t *ld);
+
+/* ---- the whole-vector statements of the host logic on device arrays: what the Fortran ddstp / dnedk /
+ * dnsk / DDASIC replace their array statements with, one call per statement or fused group (csrc/vecapi.cu cites the
+ * reference lines of each).  n = local vector length; scalars and psi / gama are host data. ---- */
+int dkb_vcopy(int64_t n, const double *x, double *y);                               /* dcopy, extern/dblas.f:48 */
+int dkb_vscale(int64_t n, double a, double *x);                                     /* dscal, extern/dblas.f:97 */
+int dkb_vscale_to(int64_t n, double a, const double *x, double *y);                 /* y = a*x, daskr.f:1919 */
+int dkb_vaxpy(int64_t n, double a, const double *x, double *y);                     /* daxpy, extern/dblas.f:1 */
+int dkb_lincomb(int64_t n, double a, const double *x, double b, const double *y, double *z);   /* z = a*x + b*y */
+int dkb_ddot(int64_t n, const double *x, const double *y, double *result);          /* ddot, extern/dblas.f:138 */
+/* ddawts + dinvwt, src/daskr_new.f90:715-780 (+ the vt mask of daskr.f:1755 when vt != NULL).  iwt = info(2): 0 ->
+ * rtol, atol host scalars; 1 -> device vectors.  *ier = first non-positive weight (1-based) or 0. */
+int dkb_ewt_set_invert(int64_t n, int iwt, const double *rtol, const double *atol, const double *y, double *wt,
+                       double *vt, const int *id, int *ier);
+int dkb_mask_vt(int64_t n, const int *id, const double *wt, double *vt);            /* vt = max(id,0)*wt, daskr.f:1755 */
+/* ddatrp, src/daskr_new.f90:782-826: phi column j at phi + j*ldphi, psi = host psi(1:kold+1) */
+int dkb_interp(int64_t n, double t, double tout, int kold, const double *phi, int64_t ldphi, const double *psi,
+               double *yout, double *ypout);
+/* predictor, dnedk:2808-2813: y = sum phi(:,j), yprime = sum gama(j)*phi(:,j); gama = host gama(1:kp1) */
+int dkb_predict(int64_t n, int kp1, const double *phi, int64_t ldphi, const double *gama, double *y, double *yprime);
+int dkb_newton_update(int64_t n, const double *delta, double cj, double *y, double *e, double *yprime);   /* dnsk:2988-2990 */
+int dkb_phi_update(int64_t n, int kp1, int write_kp2, double *phi, int64_t ldphi, const double *e);       /* ddstp:458-466 */
+/* ddstp:360-378: ||e||, ||phi(:,kp1)+e||, ||phi(:,k)+phi(:,kp1)+e|| (nn = 1..3 of them) in one pass */
+int dkb_error_norms(int64_t n, int nn, const double *e, const double *rwt, const double *phi_kp1, const double *phi_k,
+                    double *out);
+
 /* dslvk, src/daskr_new.f90:3036-3165.  Device arrays y, ydot, savr, x, ewt of
  * length neq; counters are accumulated into iwm(12,16,20,21) like the reference. */
 void dkb_dslvk(const int *neq, const double *y, const double *t, const double *ydot,

@@ -33,3 +33,15 @@ if hasattr(L, "dkb_debug_gs_clocks"):
     for t in range(0, 72, 6):
         w = v[t*8:t*8+6]
         if w[0]: print("t=%d: A %d  wait+halo+zin %d  B %d  sync %d  edge+C %d  total %d cycles" % (t, w[1]-w[0], w[2]-w[1], w[3]-w[2], w[4]-w[3], w[5]-w[4], w[5]-w[0]))
+
+if hasattr(L, "dkb_debug_gss_clocks"):
+    n = 4096 * 8
+    out = (ctypes.c_longlong * n)()
+    call(); L.dkb_sync(); L.dkb_debug_gss_clocks(out, n)
+    v = np.array(list(out)).reshape(4096, 8)
+    nb = (my + 52) // 8
+    tot = v[10:nb-10]
+    d = np.diff(tot[:, 0])
+    f = lambda a, b: (tot[:, a] - tot[:, b]).mean()
+    print("mean batch period %.0f clk; barrier %.0f | z loads issue %.0f | exchange loads issue %.0f | window->z stores %.0f | steps %.0f | z regs->smem %.0f | exchange poll %.0f"
+          % (d.mean(), f(1, 0), f(6, 1), f(7, 6), f(2, 7), f(3, 2), f(4, 3), f(5, 4)))
