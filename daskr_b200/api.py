@@ -37,7 +37,7 @@ EXPORTS = [
     "dkb_dgefa_batched", "dkb_dgesl_batched", "dkb_malloc", "dkb_free", "dkb_memcpy_h2d", "dkb_memcpy_d2h",
     "dkb_memcpy_d2d", "dkb_memset", "dkb_prof_enable", "dkb_prof_reset", "dkb_prof_get", "dkb_launch_count", "dkb_krylov_stats", "dkb_reorth_stats", "dkb_alloc_workspace", "dkb_workspace_get",
     "dkb_vcopy", "dkb_vscale", "dkb_vscale_to", "dkb_vaxpy", "dkb_lincomb", "dkb_ddot", "dkb_ewt_set_invert", "dkb_mask_vt",
-    "dkb_interp", "dkb_predict", "dkb_newton_update", "dkb_phi_update", "dkb_error_norms",
+    "dkb_jac_rbdpre", "dkb_psol_rbdpre_tiles", "dkb_interp", "dkb_predict", "dkb_newton_update", "dkb_phi_update", "dkb_error_norms",
 ]
 
 

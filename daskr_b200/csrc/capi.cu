@@ -871,9 +871,9 @@ int dkb_debug_time_datv(int level, int variant, int reps, double *ms)
     cudaEvent_t a, b;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
-    web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);   // warm
+    web_datv_fused(c->v[0], 1.0, c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);   // warm
     cudaEventRecord(a, c->stream);
-    for (int i = 0; i < reps; ++i) web_datv_fused(c->v[0], c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);
+    for (int i = 0; i < reps; ++i) web_datv_fused(c->v[0], 1.0, c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->wp, c->iwp, c->v[1], 1);
     cudaEventRecord(b, c->stream);
     cudaEventSynchronize(b);
     float t = 0.f;

@@ -41,7 +41,7 @@ void datv_fused_upload_tables(const WebPar &p)
 // MODE 2: the plain residual, vnext = G(y, ydot)                                   (res, example_web.f90:190-224).
 template <int NS, int DF_TY, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(DF_TX * DF_TY, MINB)
-web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
+web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, const double *__restrict__ wt, double wscale,
                        const double *__restrict__ y, const double *__restrict__ ydot,
                        const double *__restrict__ savr, double cj, const double *__restrict__ lut,
                        const int *__restrict__ pt, double *__restrict__ vnext)
@@ -96,7 +96,7 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
                     if (yo[u] >= 0) YDT[yo[u]] = ryd[u];
                 } else {
                     const double wgt = wscale * rwt[u];
-                    const double vtmp = rv[u] / wgt;               // vtemp = v/wght
+                    const double vtmp = (vscale * rv[u]) / wgt;    // vtemp = v/wght, v = vscale * (unnormalised basis vector)
                     Z[zo[u]] = ry[u] + vtmp;                       // z = y + vtemp
                     if (yo[u] >= 0) YDT[yo[u]] = ryd[u] + vtmp * cj;   // ydottemp = ydot + vtemp*cj
                 }
@@ -210,7 +210,7 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, const double *__r
 }
 
 template <int NS, int DF_TY, int MINB, int MODE = 0>
-static bool launch_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+static bool launch_single(const WebDev &w, const double *v, double vscale, const double *wt, double wscale, const double *y,
                           const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
                           double *vnext)
 {
@@ -223,12 +223,12 @@ static bool launch_single(const WebDev &w, const double *v, const double *wt, do
         attr_set = true;
     }
     const int tiles = (w.mx / DF_TX) * ((w.my + DF_TY - 1) / DF_TY);
-    web_datv_single_kernel<NS, DF_TY, MINB, MODE><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    web_datv_single_kernel<NS, DF_TY, MINB, MODE><<<tiles, DF_THREADS, sh, g_ctx->stream>>>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
     g_ctx->launches++;
     return true;
 }
 
-bool web_datv_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+bool web_datv_single(const WebDev &w, const double *v, double vscale, const double *wt, double wscale, const double *y,
                      const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
                      double *vnext)
 {
@@ -236,17 +236,17 @@ bool web_datv_single(const WebDev &w, const double *v, const double *wt, double 
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
     ProfScope ps(PROF_DATV1);
     switch (w.ns) {
-    case 2: return launch_single<2, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 4: return launch_single<4, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 8: return launch_single<8, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 10: return launch_single<10, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 12: return launch_single<12, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-    case 16: return launch_single<16, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 2: return launch_single<2, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 4: return launch_single<4, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 8: return launch_single<8, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 10: return launch_single<10, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 12: return launch_single<12, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+    case 16: return launch_single<16, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
     case 20:
         switch (g_ctx->debug_variant) {
-        case 1: return launch_single<20, 4, 3>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-        case 2: return launch_single<20, 8, 2>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
-        default: return launch_single<20, 4, 4>(w, v, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);   // 128 regs, 16 warps/SM: fastest measured
+        case 1: return launch_single<20, 4, 3>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        case 2: return launch_single<20, 8, 2>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);
+        default: return launch_single<20, 4, 4>(w, v, vscale, wt, wscale, y, ydot, savr, cj, lut, pt, vnext);   // 128 regs, 16 warps/SM: fastest measured
         }
     default: return false;
     }
@@ -254,12 +254,12 @@ bool web_datv_single(const WebDev &w, const double *v, const double *wt, double 
 
 // The residual alone with the same staging: mode 1 = datv's perturbed residual minus savr, mode 2 = plain res.
 // Same eligibility as web_datv_single; the caller falls back to web_restile_kernel otherwise.
-bool web_resid_single(const WebDev &w, int mode, const double *v, const double *wt, double wscale, const double *y,
+bool web_resid_single(const WebDev &w, int mode, const double *v, double vscale, const double *wt, double wscale, const double *y,
                       const double *ydot, const double *savr, double cj, double *out)
 {
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
-#define RS(N) case N: return mode == 1 ? launch_single<N, 4, 4, 1>(w, v, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out) \
-                                       : launch_single<N, 4, 4, 2>(w, v, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+#define RS(N) case N: return mode == 1 ? launch_single<N, 4, 4, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out) \
+                                       : launch_single<N, 4, 4, 2>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
     switch (w.ns) {
         RS(2) RS(4) RS(8) RS(10) RS(12) RS(16) RS(20)
     default: return false;

@@ -173,7 +173,7 @@ void v_phi_update(i64 n, int kp1, int write_kp2, double *const *phi, const doubl
 void v_ewt(i64 n, int iwt, double rtol, double atol, const double *d_rtol, const double *d_atol,
            const double *y, double *wt, double *vt, const int *id, int *first_bad);
 // datv unfused pieces (:3493-3498, 3509, 3518)
-void v_datv_pre(i64 n, const double *v, const double *wt, double wscale, const double *y,
+void v_datv_pre(i64 n, const double *v, double vscale, const double *wt, double wscale, const double *y,
                 const double *ydot, double cj, double *vtemp, double *ydottemp, double *z);
 // Newton update (dnsk:2988-2993): y-=delta, e-=delta, ydot-=cj*delta; returns wrms partials
 void v_newton_update(i64 n, const double *delta, double cj, double *y, double *e, double *ydot);
@@ -182,11 +182,15 @@ void v_dyypnw(i64 n, const double *y, const double *yp, double cj, double rl, co
               int icopt, const int *id, double *ynew, double *ypnew);
 void v_min0(i64 n, const double *y, double *delta);                       // delta = min(y,0)
 // solution assembly (dspigm:3413-3417) z = (sum_i r_i v_i)/(wscale*wt); x = x + z (or x = z)
-void v_gmres_solution(i64 n, int ll, double *const *v, const double *r, const double *wt,
+void v_gmres_solution(i64 n, int ll, double *const *v, const double *vs, const double *r, const double *wt,
                       double wscale, double *x, int first);
 // restart residual (dspigm:3381-3401): dl = (v1; dl = s*dl + c*v_{i+1} ...) * scale
-void v_gmres_dl(i64 n, int maxl, double *const *v, const double *q, double snormw, double scale,
+void v_gmres_dl(i64 n, int maxl, double *const *v, const double *vs, const double *q, double snormw, double scale,
                 double *dl);
+// the same with a normalisation factor on x / y: the Krylov basis is kept unnormalised (krylov.cu)
+void v_axpy_s(i64 n, double a, const double *x, double s, double *y);                                 // y = y + a*(s*x)
+void v_lin2_s(i64 n, double a, const double *x, double b, const double *y, double s, double *z);      // z = a*x + b*(s*y)
+void r_dot_s(i64 n, const double *x, double sx, const double *y, int slot);                           // (sx*x).y
 
 // Reductions: results land in g_ctx->d_scal[slot...] (allreduced across ranks), host reads
 // them with scal_fetch().  All deterministic for a fixed n / grid.
@@ -196,10 +200,10 @@ void r_max(i64 n, const double *x, int slot);
 bool r_wrms3(i64 n, int nn, const double *e, const double *rwt, const double *phi_kp1, const double *phi_k, double *out);   // ddstp error estimates, one pass
 void r_cnstr(i64 n, const double *y, const double *ynew, const int *icnstr, int slot);   // dcnstr: [rdymx, hard flag]
 void v_cnst0(i64 n, const double *y, const int *icnstr, int *d_flag);                   // dcnst0: atomicMin(first bad index + 1)                                  // max_i x[i]
-void r_dot2(i64 n, const double *vnew, const double *v1, int slot);            // [vnew.vnew, v1.vnew]
-void r_axpy_dot(i64 n, double *vnew, const double *vi, int hslot, const double *vnext,
-                int slot);   // vnew -= h*vi ; out = vnext.vnew
-void r_axpy_nrm(i64 n, double *vnew, const double *vi, int hslot, int slot);  // vnew -= h*vi ; out = vnew.vnew
+void r_dot2(i64 n, const double *vnew, const double *v1, double s1, int slot);            // [vnew.vnew, (s1*v1).vnew]
+void r_axpy_dot(i64 n, double *vnew, const double *vi, double si, int hslot, const double *vnext, double sn,
+                int slot);   // vnew -= h*(si*vi) ; out = (sn*vnext).vnew
+void r_axpy_nrm(i64 n, double *vnew, const double *vi, double si, int hslot, int slot);  // vnew -= h*(si*vi) ; out = vnew.vnew
 void r_wrms_parts(i64 n, const double *v, const double *rwt, int slot);        // [sum (v*rwt)^2 , max|v*rwt|]
 void scal_fetch(int slot, int count, double *out);   // stream-ordered D2H + sync
 double r_wrms(i64 n, const double *v, const double *rwt);   // ddwnrm :828-868, global N
@@ -236,12 +240,12 @@ void allreduce_sum_buf(double *buf, i64 n);   // gs.cu: z := GS(A_S) z, x = N wo
 void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd,
                     int *d_first_flag);
 // fused datv: vnext = wscale*wt * P^-1 ( G(y + v/(wscale*wt), ydot + cj*v/(wscale*wt)) - savr )
-int web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+int web_datv_fused(const double *v, double vscale, const double *wt, double wscale, const double *y, const double *ydot,
                    const double *savr, double cj, const double *bd, const int *ipbd, double *vnext, int jpre);
 void heat_res_launch(const double *u, const double *udot, double *delta);
 void heat_jac_launch(const double *u, const double *rewt, double cj, double *bd, int *ipbd,
                      int *d_first_flag);
-void heat_datv_fused(const double *v, const double *wt, double wscale, const double *y,
+void heat_datv_fused(const double *v, double vscale, const double *wt, double wscale, const double *y,
                      const double *ydot, const double *savr, double cj, const double *bd,
                      double *vnext);
 

@@ -50,10 +50,10 @@ struct HStatePlain {
 };
 struct HStateDatv {
     const double *y, *v, *wt;
-    double wscale;
+    double wscale, vscale;     // vscale: normalisation factor of v (the Krylov basis is kept unnormalised)
     __device__ __forceinline__ double operator()(i64 i) const
     {
-        return __ldg(y + i) + __ldg(v + i) / (wscale * __ldg(wt + i));
+        return __ldg(y + i) + (vscale * __ldg(v + i)) / (wscale * __ldg(wt + i));
     }
 };
 
@@ -92,17 +92,17 @@ __global__ void __launch_bounds__(256) heat_jac_kernel(HeatDev h, i64 n, const d
 }
 
 // fused datv (src/daskr_new.f90:3493-3518) with res and the 1x1 dgesl inlined
-__global__ void __launch_bounds__(256) heat_datv_kernel(HeatDev h, i64 n, const double *__restrict__ v,
+__global__ void __launch_bounds__(256) heat_datv_kernel(HeatDev h, i64 n, const double *__restrict__ v, double vscale,
                                                         const double *__restrict__ wt, double wscale,
                                                         const double *__restrict__ y, const double *__restrict__ ydot,
                                                         const double *__restrict__ savr, double cj,
                                                         const double *__restrict__ bd, double *__restrict__ vnext)
 {
-    HStateDatv S{y, v, wt, wscale};
+    HStateDatv S{y, v, wt, wscale, vscale};
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double wgt = wscale * __ldg(wt + i);
-        const double vtmp = __ldg(v + i) / wgt;
+        const double vtmp = (vscale * __ldg(v + i)) / wgt;
         const double zi = __ldg(y + i) + vtmp;
         const double ydt = __ldg(ydot + i) + vtmp * cj;
         double d = heat_point_res(h, S, i, zi, ydt);
@@ -132,11 +132,11 @@ void heat_jac_launch(const double *u, const double *rewt, double cj, double *bd,
     heat_jac_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, u, rewt, bd, ipbd, d_first_flag);
     COUNT_LAUNCH();
 }
-void heat_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+void heat_datv_fused(const double *v, double vscale, const double *wt, double wscale, const double *y, const double *ydot,
                      const double *savr, double cj, const double *bd, double *vnext)
 {
     DkbCtx *c = g_ctx;
-    heat_datv_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, v, wt, wscale, y, ydot,
+    heat_datv_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, v, vscale, wt, wscale, y, ydot,
                                                             savr, cj, bd, vnext);
     COUNT_LAUNCH();
 }

@@ -103,8 +103,10 @@ struct GmresArgs {
     int jpre;   // food web: ipar(1)
 };
 
-// datv, src/daskr_new.f90:3429-3520: vnext = D^-1 P^-1 (dF/dy) D v
-static void k_datv(const GmresArgs &A, const double *v, double *vnext, int *ires, int *ierr, int *nres, int *npsol)
+// datv, src/daskr_new.f90:3429-3520: vnext = D^-1 P^-1 (dF/dy) D v.  The basis vector arrives unnormalised with its
+// factor vs = 1/||.||: every kernel forms vs*v[i] on load -- the product the reference's dscal stored (dspigm:3295, 3358)
+// -- which saves the separate normalisation pass over v(:,ll+1) (16 bytes per unknown and Krylov iteration).
+static void k_datv(const GmresArgs &A, const double *v, double vs, double *vnext, int *ires, int *ierr, int *nres, int *npsol)
 {
     DkbCtx *c = g_ctx;
     ProfScope ps(PROF_DATV);
@@ -113,16 +115,16 @@ static void k_datv(const GmresArgs &A, const double *v, double *vnext, int *ires
     if (A.fused) {
         if (c->nranks > 1) halo_exchange(const_cast<double *>(v));
         if (c->problem == DKB_PROB_WEB) {
-            if (web_datv_fused(v, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, c->iwp, vnext, A.jpre) != 0) *ierr = -1;
+            if (web_datv_fused(v, vs, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, c->iwp, vnext, A.jpre) != 0) *ierr = -1;
         } else
-            heat_datv_fused(v, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, vnext);
+            heat_datv_fused(v, vs, A.wt, A.rsqrtn, A.y, A.ydot, A.savr, A.cj, c->wp, vnext);
         *nres += 1;
         *npsol += 1;
         return;
     }
     const int neq32 = (int)A.neq;
     double *vtemp = c->wk, *ydottemp = c->z;
-    v_datv_pre(A.neq, v, A.wt, A.rsqrtn, A.y, A.ydot, A.cj, vtemp, ydottemp, vnext);
+    v_datv_pre(A.neq, v, vs, A.wt, A.rsqrtn, A.y, A.ydot, A.cj, vtemp, ydottemp, vnext);
     A.res(&A.t, vnext, ydottemp, &A.cj, vtemp, ires, A.rpar, A.ipar);
     *nres += 1;
     if (*ires < 0) return;
@@ -135,20 +137,20 @@ static void k_datv(const GmresArgs &A, const double *v, double *vnext, int *ires
 }
 
 // dorth, src/daskr_new.f90:3522-3590.  Fills column ll of hes, returns snormw.
-static double k_dorth(i64 n, double *vnew, double *const *v, double *hes, int ldh, int ll, int kmp)
+static double k_dorth(i64 n, double *vnew, double *const *v, const double *vs, double *hes, int ldh, int ll, int kmp)
 {
     ProfScope ps(PROF_MGS);
     const int i0 = std::max(1, ll - kmp + 1);
     // vnorm^2 and the first coefficient in one pass, then fused (axpy_i , dot_{i+1}) passes,
     // the last one fused with the norm of the result.
-    r_dot2(n, vnew, v[i0 - 1], S_VNORM);   // S_VNORM, S_VNORM+1 (= S_H + 0 scratch)
+    r_dot2(n, vnew, v[i0 - 1], vs[i0 - 1], S_VNORM);   // S_VNORM, S_VNORM+1 (= S_H + 0 scratch)
     // r_dot2 wrote [vnorm^2, h_i0] to slots S_VNORM, S_VNORM+1; S_H == S_VNORM+1 holds h_i0.
     int hslot = S_H;
     for (int i = i0; i <= ll - 1; ++i) {
-        r_axpy_dot(n, vnew, v[i - 1], hslot, v[i], hslot + 1);
+        r_axpy_dot(n, vnew, v[i - 1], vs[i - 1], hslot, v[i], vs[i], hslot + 1);
         hslot += 1;
     }
-    r_axpy_nrm(n, vnew, v[ll - 1], hslot, S_SNORM);
+    r_axpy_nrm(n, vnew, v[ll - 1], vs[ll - 1], hslot, S_SNORM);
     double buf[DKB_MAXL_MAX + 2];
     scal_fetch(S_VNORM, S_SNORM - S_VNORM + 1, buf);   // one 144-byte readback per Krylov iteration
     const double sn2 = buf[S_SNORM - S_VNORM];
@@ -163,14 +165,14 @@ static double k_dorth(i64 n, double *vnew, double *const *v, double *hes, int ld
     double sumdsq = 0.0;
     for (int i = i0; i <= ll; ++i) {
         double d;
-        r_dot(n, v[i - 1], vnew, S_TMP);
+        r_dot_s(n, v[i - 1], vs[i - 1], vnew, S_TMP);
         scal_fetch(S_TMP, 1, &d);
         double tem = -d;
         volatile double probe2 = HES(i, ll) + tem / 1000;
         if (probe2 == HES(i, ll)) continue;
         HES(i, ll) = HES(i, ll) - tem;
         g_ctx->reorth_corrections += 1;
-        v_axpy(n, tem, v[i - 1], vnew);
+        v_axpy_s(n, tem, v[i - 1], vs[i - 1], vnew);
         sumdsq = sumdsq + tem * tem;
     }
     if (sumdsq == 0.0) return snormw;
@@ -190,6 +192,7 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
     int ierr = 0, info = 0, ll = 0;
     double prod, rho = 0.0, rnorm, snormw = 0.0, sumsq, dlnorm;
     double **v = c->v;
+    double vs[DKB_MAXL_MAX + 1];   // vs[k] = 1/||v_k||: the basis is stored unnormalised, consumers multiply on load
 
     *iflag = 0;
     *lgmr = 0;
@@ -234,7 +237,7 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
         *rhok = rnorm;
         return;
     }
-    v_scale(neq, 1.0 / rnorm, v[0]);
+    vs[0] = 1.0 / rnorm;   // :3294-3295 (tem = one/rnorm; dscal)
     for (int i = 0; i < ldh * maxl; ++i) hes[i] = 0.0;
 
     prod = 1.0;
@@ -242,14 +245,14 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
         *lgmr = ll;
         ProfScope kit(PROF_KIT);   // one Arnoldi iteration: datv + dorth (+ the normalisation of v(:,ll+1))
         c->ll_hist[ll] += 1;
-        k_datv(A, v[ll - 1], v[ll], ires, &ierr, nres, npsol);
+        k_datv(A, v[ll - 1], vs[ll - 1], v[ll], ires, &ierr, nres, npsol);
         if (*ires < 0) {
             if (first) v_zero(neq, A.x);
             return;
         }
         if (ierr != 0) goto L300;
 
-        snormw = k_dorth(neq, v[ll], v, hes, ldh, ll, kmp);
+        snormw = k_dorth(neq, v[ll], v, vs, hes, ldh, ll, kmp);
         HES(ll + 1, ll) = snormw;
 
         info = h_dheqr_update(hes, ldh, ll, q);
@@ -260,8 +263,8 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
         if ((ll > kmp) && (kmp < maxl)) {
             // incomplete orthogonalisation: update dl and use its norm (:3329-3350)
             if (ll == kmp + 1) {
-                v_copy(neq, v[0], c->dl);
-                for (int i = 1; i <= kmp; ++i) v_lin2(neq, q[2 * i - 1], c->dl, q[2 * i - 2], v[i], c->dl);
+                v_scale_to(neq, vs[0], v[0], c->dl);
+                for (int i = 1; i <= kmp; ++i) v_lin2_s(neq, q[2 * i - 1], c->dl, q[2 * i - 2], v[i], vs[i], c->dl);
             }
             v_lin2(neq, q[2 * ll - 1], c->dl, q[2 * ll - 2] / snormw, v[ll], c->dl);
             dlnorm = r_nrm2(neq, c->dl);
@@ -269,7 +272,7 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
         }
         if (rho <= A.epslin) goto L200;
         if (ll == maxl) goto L100;
-        v_scale(neq, 1.0 / snormw, v[ll]);
+        vs[ll] = 1.0 / snormw;   // :3357-3359 (tem = one/snormw; dscal): applied by the consumers of v(:,ll+1)
     }
 
 L100:
@@ -283,7 +286,7 @@ L150:
     *iflag = 1;
     // restart residual dl (irst > 0 always, dslvk:3093)
     if (kmp == maxl)
-        v_gmres_dl(neq, maxl, v, q, snormw, rnorm * prod, c->dl);
+        v_gmres_dl(neq, maxl, v, vs, q, snormw, rnorm * prod, c->dl);
     else
         v_scale(neq, rnorm * prod, c->dl);
 
@@ -293,7 +296,7 @@ L200: {
     for (int i = 0; i <= ll; ++i) r[i] = 0.0;
     r[0] = rnorm;
     h_dhels(hes, ldh, ll, q, r);
-    v_gmres_solution(neq, ll, v, r, A.wt, A.rsqrtn, A.x, first);
+    v_gmres_solution(neq, ll, v, vs, r, A.wt, A.rsqrtn, A.x, first);
     *rhok = rho;
     return;
 }

@@ -53,6 +53,10 @@ struct FLin2 { double a, b; const double *x, *y; double *z; __device__ void oper
 struct FMul { const double *x, *w; double *y; __device__ void operator()(i64 i) const { y[i] = x[i] * w[i]; } };
 struct FSub { const double *x, *y; double *z; __device__ void operator()(i64 i) const { z[i] = x[i] - y[i]; } };
 
+struct FAxpyS { double a, s; const double *x; double *y; __device__ void operator()(i64 i) const { y[i] = y[i] + a * (s * x[i]); } };
+struct FLin2S { double a, b, s; const double *x, *y; double *z; __device__ void operator()(i64 i) const { z[i] = a * x[i] + b * (s * y[i]); } };
+void v_axpy_s(i64 n, double a, const double *x, double s, double *y) { launch_map(FAxpyS{a, s, x, y}, n); }
+void v_lin2_s(i64 n, double a, const double *x, double b, const double *y, double s, double *z) { launch_map(FLin2S{a, b, s, x, y, z}, n); }
 void v_copy(i64 n, const double *x, double *y) { if (x != y) launch_map(FCopy{x, y}, n); }
 void v_zero(i64 n, double *y) { launch_map(FZero{y}, n); }
 void v_scale(i64 n, double a, double *x) { launch_map(FScale{a, x}, n); }
@@ -158,20 +162,20 @@ void v_ewt(i64 n, int iwt, double rtol, double atol, const double *d_rtol, const
 // datv:3493-3498 (unfused form used with user callbacks)
 struct FDatvPre {
     const double *v, *wt, *y, *ydot;
-    double wscale, cj;
+    double vscale, wscale, cj;
     double *vtemp, *ydottemp, *z;
     __device__ void operator()(i64 i) const
     {
-        double vt = v[i] / (wscale * wt[i]);
+        double vt = (vscale * v[i]) / (wscale * wt[i]);   // v(:,ll) is kept unnormalised: vscale = 1/snormw (dspigm:3358)
         vtemp[i] = vt;
         ydottemp[i] = ydot[i] + vt * cj;
         z[i] = y[i] + vt;
     }
 };
-void v_datv_pre(i64 n, const double *v, const double *wt, double wscale, const double *y,
+void v_datv_pre(i64 n, const double *v, double vscale, const double *wt, double wscale, const double *y,
                 const double *ydot, double cj, double *vtemp, double *ydottemp, double *z)
 {
-    launch_map(FDatvPre{v, wt, y, ydot, wscale, cj, vtemp, ydottemp, z}, n);
+    launch_map(FDatvPre{v, wt, y, ydot, vscale, wscale, cj, vtemp, ydottemp, z}, n);
 }
 
 struct FNewton {
@@ -227,7 +231,7 @@ void v_min0(i64 n, const double *y, double *delta) { launch_map(FMin0{y, delta},
 struct FGmresSol {
     int ll, first;
     const double *v[DKB_MAXL_MAX];
-    double r[DKB_MAXL_MAX];
+    double r[DKB_MAXL_MAX], vs[DKB_MAXL_MAX];   // vs: normalisation factors of the basis vectors (kept unnormalised in memory)
     const double *wt;
     double wscale;
     double *x;
@@ -236,12 +240,12 @@ struct FGmresSol {
         double z = 0.0;
 #pragma unroll 1
         for (int k = 0; k < ll; ++k)
-            if (r[k] != 0.0) z = z + r[k] * v[k][i];   // daxpy skips da == 0
+            if (r[k] != 0.0) z = z + r[k] * (vs[k] * v[k][i]);   // daxpy skips da == 0
         z = z / (wscale * wt[i]);
         x[i] = first ? (0.0 + z) : (x[i] + z);
     }
 };
-void v_gmres_solution(i64 n, int ll, double *const *v, const double *r, const double *wt,
+void v_gmres_solution(i64 n, int ll, double *const *v, const double *vs, const double *r, const double *wt,
                       double wscale, double *x, int first)
 {
     FGmresSol f;
@@ -250,6 +254,7 @@ void v_gmres_solution(i64 n, int ll, double *const *v, const double *r, const do
     for (int k = 0; k < DKB_MAXL_MAX; ++k) {
         f.v[k] = v[k < ll ? k : 0];
         f.r[k] = k < ll ? r[k] : 0.0;
+        f.vs[k] = k < ll ? vs[k] : 0.0;
     }
     f.wt = wt;
     f.wscale = wscale;
@@ -262,22 +267,24 @@ void v_gmres_solution(i64 n, int ll, double *const *v, const double *r, const do
 struct FGmresDl {
     int maxl;
     const double *v[DKB_MAXL_MAX + 1];
-    double s[DKB_MAXL_MAX], c[DKB_MAXL_MAX];
+    double s[DKB_MAXL_MAX], c[DKB_MAXL_MAX], vs[DKB_MAXL_MAX];
     double scale;
     double *dl;
     __device__ void operator()(i64 i) const
     {
-        double d = v[0][i];
+        double d = vs[0] * v[0][i];
 #pragma unroll 1
-        for (int k = 1; k <= maxl; ++k) d = s[k - 1] * d + c[k - 1] * v[k][i];
+        for (int k = 1; k < maxl; ++k) d = s[k - 1] * d + c[k - 1] * (vs[k] * v[k][i]);
+        d = s[maxl - 1] * d + c[maxl - 1] * v[maxl][i];   // v(:,maxl+1) is not normalised in the reference either (:3395-3398)
         dl[i] = scale * d;
     }
 };
-void v_gmres_dl(i64 n, int maxl, double *const *v, const double *q, double snormw, double scale, double *dl)
+void v_gmres_dl(i64 n, int maxl, double *const *v, const double *vs, const double *q, double snormw, double scale, double *dl)
 {
     FGmresDl f;
     f.maxl = maxl;
     for (int k = 0; k <= DKB_MAXL_MAX; ++k) f.v[k] = v[k <= maxl ? k : 0];
+    for (int k = 0; k < DKB_MAXL_MAX; ++k) f.vs[k] = k < maxl ? vs[k] : 0.0;
     for (int k = 1; k <= maxl; ++k) {
         f.s[k - 1] = q[2 * k - 1];
         f.c[k - 1] = (k < maxl) ? q[2 * k - 2] : q[2 * k - 2] / snormw;
@@ -379,39 +386,50 @@ struct RDot {
     __device__ void init() {}
     __device__ void operator()(i64 i, double (&a)[1]) const { a[0] = a[0] + x[i] * y[i]; }
 };
+// The basis vectors v(:,1:ll) stay unnormalised in memory; s1 / si / sn are their normalisation factors 1/||.||
+// (dspigm:3295, 3358): s*v[i] is exactly the value the reference's dscal stored.
 struct RDot2 {
     const double *vnew, *v1;
+    double s1;
     __device__ void init() {}
     __device__ void operator()(i64 i, double (&a)[2]) const
     {
         double w = vnew[i];
         a[0] = a[0] + w * w;
-        a[1] = a[1] + v1[i] * w;
+        a[1] = a[1] + (s1 * v1[i]) * w;
     }
 };
 struct RAxpyDot {
     double *vnew;
     const double *vi, *hptr, *vnext;
+    double si, sn;
     double h;
     __device__ void init() { h = *hptr; }
     __device__ void operator()(i64 i, double (&a)[1]) const
     {
-        double w = vnew[i] - h * vi[i];   // dorth:3565-3566 (tem = -hes; vnew += tem*v_i)
+        double w = vnew[i] - h * (si * vi[i]);   // dorth:3565-3566 (tem = -hes; vnew += tem*v_i)
         vnew[i] = w;
-        a[0] = a[0] + vnext[i] * w;
+        a[0] = a[0] + (sn * vnext[i]) * w;
     }
 };
 struct RAxpyNrm {
     double *vnew;
     const double *vi, *hptr;
+    double si;
     double h;
     __device__ void init() { h = *hptr; }
     __device__ void operator()(i64 i, double (&a)[1]) const
     {
-        double w = vnew[i] - h * vi[i];
+        double w = vnew[i] - h * (si * vi[i]);
         vnew[i] = w;
         a[0] = a[0] + w * w;
     }
+};
+struct RDotS {
+    const double *x, *y;
+    double sx;
+    __device__ void init() {}
+    __device__ void operator()(i64 i, double (&a)[1]) const { a[0] = a[0] + (sx * x[i]) * y[i]; }
 };
 struct RWrms {
     const double *v, *rwt;
@@ -507,19 +525,24 @@ void r_dot(i64 n, const double *x, const double *y, int slot)
     launch_reduce<1, 0>(RDot{x, y}, n, slot);
     allreduce_sum(slot, 1);
 }
-void r_dot2(i64 n, const double *vnew, const double *v1, int slot)
+void r_dot_s(i64 n, const double *x, double sx, const double *y, int slot)
 {
-    launch_reduce<2, 0>(RDot2{vnew, v1}, n, slot);
-    allreduce_sum(slot, 2);
-}
-void r_axpy_dot(i64 n, double *vnew, const double *vi, int hslot, const double *vnext, int slot)
-{
-    launch_reduce<1, 0>(RAxpyDot{vnew, vi, g_ctx->d_scal + hslot, vnext, 0.0}, n, slot);
+    launch_reduce<1, 0>(RDotS{x, y, sx}, n, slot);
     allreduce_sum(slot, 1);
 }
-void r_axpy_nrm(i64 n, double *vnew, const double *vi, int hslot, int slot)
+void r_dot2(i64 n, const double *vnew, const double *v1, double s1, int slot)
 {
-    launch_reduce<1, 0>(RAxpyNrm{vnew, vi, g_ctx->d_scal + hslot, 0.0}, n, slot);
+    launch_reduce<2, 0>(RDot2{vnew, v1, s1}, n, slot);
+    allreduce_sum(slot, 2);
+}
+void r_axpy_dot(i64 n, double *vnew, const double *vi, double si, int hslot, const double *vnext, double sn, int slot)
+{
+    launch_reduce<1, 0>(RAxpyDot{vnew, vi, g_ctx->d_scal + hslot, vnext, si, sn, 0.0}, n, slot);
+    allreduce_sum(slot, 1);
+}
+void r_axpy_nrm(i64 n, double *vnew, const double *vi, double si, int hslot, int slot)
+{
+    launch_reduce<1, 0>(RAxpyNrm{vnew, vi, g_ctx->d_scal + hslot, si, 0.0}, n, slot);
     allreduce_sum(slot, 1);
 }
 void r_wrms_parts(i64 n, const double *v, const double *rwt, int slot)

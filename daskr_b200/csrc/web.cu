@@ -94,7 +94,7 @@ template <int NS> struct RT {
 
 template <int NS, bool DATV>
 __global__ void __launch_bounds__(RT<NS>::THREADS)
-web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restrict__ wt, double wscale,
+web_restile_kernel(WebDev w, const double *__restrict__ v, double vscale, const double *__restrict__ wt, double wscale,
                    const double *__restrict__ y, const double *__restrict__ ydot, double cj,
                    const double *__restrict__ sub, double *__restrict__ out)
 {
@@ -144,7 +144,7 @@ web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restr
             double z = ryy[ry];
             if (DATV) {
                 const double wgt = wscale * rw[ry];
-                const double vtmp = rv[ry] / wgt;              // vtemp = v/wght            (datv:3493)
+                const double vtmp = (vscale * rv[ry]) / wgt;   // vtemp = v/wght            (datv:3493)
                 z = ryy[ry] + vtmp;                            // z = y + vtemp             (:3498)
                 ydt[ry] = ydt[ry] + vtmp * cj;                 // ydottemp = ydot + vtemp*cj (:3497)
             }
@@ -166,7 +166,7 @@ web_restile_kernel(WebDev w, const double *__restrict__ v, const double *__restr
         if (rowok && hgx >= 0 && hgx < w.mx) {
             const i64 g = (i64)gy * mxns + (i64)hgx * NS + hi;   // may address the slab halo rows
             double z = __ldg(y + g);
-            if (DATV) z = z + __ldg(v + g) / (wscale * __ldg(wt + g));
+            if (DATV) z = z + (vscale * __ldg(v + g)) / (wscale * __ldg(wt + g));
             Z[((ry + 1) * ZX + (hx + 1)) * NS + hi] = z;
         }
     }
@@ -306,7 +306,7 @@ static int grp_grid(i64 npts, int G, int block, int per_sm)
     }
 
 template <int NS, bool DATV>
-static void restile_launch(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+static void restile_launch(const WebDev &w, const double *v, double vscale, const double *wt, double wscale, const double *y,
                            const double *ydot, double cj, const double *sub, double *out)
 {
     static bool attr_set = false;
@@ -317,15 +317,15 @@ static void restile_launch(const WebDev &w, const double *v, const double *wt, d
         attr_set = true;
     }
     const int tiles = ((w.mx + TX - 1) / TX) * ((w.my + RT_TY - 1) / RT_TY);
-    web_restile_kernel<NS, DATV><<<tiles, RT<NS>::THREADS, sh, g_ctx->stream>>>(w, v, wt, wscale, y, ydot, cj, sub, out);
+    web_restile_kernel<NS, DATV><<<tiles, RT<NS>::THREADS, sh, g_ctx->stream>>>(w, v, vscale, wt, wscale, y, ydot, cj, sub, out);
     COUNT_LAUNCH();
 }
 
 void web_res_launch(const double *c, const double *cdot, double *delta)
 {
     WebDev w = make_webdev();
-    if (g_ctx->opt_fused >= 2 && web_resid_single(w, 2, nullptr, nullptr, 1.0, c, cdot, nullptr, 0.0, delta)) return;
-#define CALL(N) restile_launch<N, false>(w, nullptr, nullptr, 1.0, c, cdot, 0.0, nullptr, delta)
+    if (g_ctx->opt_fused >= 2 && web_resid_single(w, 2, nullptr, 1.0, nullptr, 1.0, c, cdot, nullptr, 0.0, delta)) return;
+#define CALL(N) restile_launch<N, false>(w, nullptr, 1.0, nullptr, 1.0, c, cdot, 0.0, nullptr, delta)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
 }
@@ -417,19 +417,19 @@ void web_jac_groups_launch(const double *c, const double *rewt, double *bd)
 // "- savr" and "* wght" statements folded into its load / store phases.
 // jpre = 3 (example_web.f90:346-391, the shipped setting): the Gauss-Seidel factor runs between the two, on
 // vtemp - savr (the subtraction folded into the residual kernel's store).
-int web_datv_fused(const double *v, const double *wt, double wscale, const double *y, const double *ydot,
+int web_datv_fused(const double *v, double vscale, const double *wt, double wscale, const double *y, const double *ydot,
                    const double *savr, double cj, const double *bd, const int *ipbd, double *vnext, int jpre)
 {
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
     // one kernel when the mesh allows it (warp = 32 consecutive points of a row = one LU tile)
-    if (jpre == 1 && x->opt_fused >= 2 && web_datv_single(w, v, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)) return 0;
+    if (jpre == 1 && x->opt_fused >= 2 && web_datv_single(w, v, vscale, wt, wscale, y, ydot, savr, cj, bd, ipbd, vnext)) return 0;
     double *vtemp = x->z;
     const double *sub = (jpre == 1) ? nullptr : savr;
     {
         ProfScope ps(PROF_RESDATV);
-        if (!(jpre != 1 && x->opt_fused >= 2 && web_resid_single(w, 1, v, wt, wscale, y, ydot, savr, cj, vtemp))) {
-#define CALL(N) restile_launch<N, true>(w, v, wt, wscale, y, ydot, cj, sub, vtemp)
+        if (!(jpre != 1 && x->opt_fused >= 2 && web_resid_single(w, 1, v, vscale, wt, wscale, y, ydot, savr, cj, vtemp))) {
+#define CALL(N) restile_launch<N, true>(w, v, vscale, wt, wscale, y, ydot, cj, sub, vtemp)
             WEB_DISPATCH(w.ns, CALL)
 #undef CALL
         }

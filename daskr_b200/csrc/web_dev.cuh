@@ -14,12 +14,12 @@ WebDev make_webdev();
 void datv_fused_upload_tables(const WebPar &p);
 void jac2_upload_tables(const WebPar &p);
 // residual only, same staging as the single datv kernel (datv_fused.cu): mode 1 = perturbed - savr, 2 = plain res
-bool web_resid_single(const WebDev &w, int mode, const double *v, const double *wt, double wscale, const double *y,
+bool web_resid_single(const WebDev &w, int mode, const double *v, double vscale, const double *wt, double wscale, const double *y,
                       const double *ydot, const double *savr, double cj, double *out);
 // two-phase FD + LU block Jacobian (jac2.cu)
 bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
               int *d_first_flag);
 // single-kernel datv; returns false if the mesh / ns is not eligible (caller falls back)
-bool web_datv_single(const WebDev &w, const double *v, const double *wt, double wscale, const double *y,
+bool web_datv_single(const WebDev &w, const double *v, double vscale, const double *wt, double wscale, const double *y,
                      const double *ydot, const double *savr, double cj, const double *lut, const int *pt,
                      double *vnext);

@@ -69,6 +69,12 @@ typedef void (*dkb_psol_t)(const int *neq, const double *t, const double *y,
                            int *iwp, double *b, const double *epslin, int *ierr,
                            double *rpar, int *ipar);
 
+/* rblock of jac_rbdpre, src/daskr_rbdpre.f90:176-189, batched over the mesh: r = R(t, u) for ALL mesh points in one call
+ * (u, r device arrays of ns*mx*my doubles, species fastest, my = this rank's rows; one launch on dkb_stream()).
+ * `user` is passed through untouched. */
+typedef void (*dkb_rblock_t)(const double *t, const int *mx, const int *my, const int *ns, const double *u, double *r,
+                             void *user);
+
 /* root functions, src/daskr.f:908-934: rt(neq,t,y,yp,nrt,rval,rpar,ipar); y, yp device, rval host */
 typedef void (*dkb_rt_t)(const int *neq, const double *t, const double *y, const double *yp,
                          const int *nrt, double *rval, double *rpar, int *ipar);
@@ -207,6 +213,13 @@ void dkb_dslvk(const int *neq, const double *y, const double *t, const double *y
                double *rhok, double *rpar, int *ipar);
 /* ddwnrm, src/daskr_new.f90:828-868 (device v, rwt) */
 double dkb_ddwnrm(const int *neq, const double *v, const double *rwt);
+/* jac_rbdpre, src/daskr_rbdpre.f90:158-251, for any user reaction term: same arguments plus the `user` pointer handed to
+ * the batched rblock; r1 is N doubles of scratch.  Writes bd / ipbd in the reference's layout (block p at bd + p*ns*ns,
+ * column-major; pivots 1-based at ipbd + p*ns); *ierr = dgefa's info of the first failing block (0: none). */
+void dkb_jac_rbdpre(const double *t, double *u, const double *r0, dkb_rblock_t rblock, void *user, double *r1,
+                    const double *rewt, const double *cj, double *bd, int *ipbd, int *ierr);
+/* psol_rbdpre on the tile-interleaved blocks (dkb_rbd_from_reference / the built-in jac routines): streaming solve */
+void dkb_psol_rbdpre_tiles(double *b, const double *rwp, const int *iwp);
 /* psol_rbdpre, src/daskr_rbdpre.f90:253-279, on device arrays in the reference's bd / ipbd
  * layout (block p at bd+p*ns*ns column-major, pivots 1-based at ipbd+p*ns) */
 void dkb_psol_rbdpre(double *b, const double *bd, const int *ipbd);

@@ -65,7 +65,7 @@ def test_weights_and_mask(env):
     assert L.dkb_mask_vt(N, did.ptr, dwt.ptr, dvt.ptr) == 0
     got, w2 = dvt.to_host(np.float64, (N,)), dwt.to_host(np.float64, (N,))
     ok = np.arange(N) != 4711
-    assert np.array_equal(got[ok], (np.maximum(idv, 0) * w2)[ok])
+    assert np.array_equal(got[ok], np.maximum(idv, 0)[ok] * w2[ok])
 
 
 def test_predict_interp_phi_newton(env):
