@@ -182,20 +182,39 @@ __global__ void __launch_bounds__(256) tpp_relayout_kernel(int ns, i64 npts, dou
 }
 
 #define TPP_DISPATCH(ns, CALL)                                                                       \
-    switch (ns) {                                                                                    \
-    case 2: { CALL(2); } break;                                                                      \
-    case 3: { CALL(3); } break;                                                                      \
-    case 4: { CALL(4); } break;                                                                      \
-    case 5: { CALL(5); } break;                                                                      \
-    case 6: { CALL(6); } break;                                                                      \
-    case 8: { CALL(8); } break;                                                                      \
-    case 10: { CALL(10); } break;                                                                    \
-    case 12: { CALL(12); } break;                                                                    \
-    case 16: { CALL(16); } break;                                                                    \
-    case 20: { CALL(20); } break;                                                                    \
-    case 24: { CALL(24); } break;                                                                    \
-    case 32: { CALL(32); } break;                                                                    \
-    default: return dkb_fail(DKB_E_UNSUPPORTED, "block size ns=%d not instantiated", ns);            \
+    switch (ns) { \
+    case 2: { CALL(2); } break; \
+    case 3: { CALL(3); } break; \
+    case 4: { CALL(4); } break; \
+    case 5: { CALL(5); } break; \
+    case 6: { CALL(6); } break; \
+    case 7: { CALL(7); } break; \
+    case 8: { CALL(8); } break; \
+    case 9: { CALL(9); } break; \
+    case 10: { CALL(10); } break; \
+    case 11: { CALL(11); } break; \
+    case 12: { CALL(12); } break; \
+    case 13: { CALL(13); } break; \
+    case 14: { CALL(14); } break; \
+    case 15: { CALL(15); } break; \
+    case 16: { CALL(16); } break; \
+    case 17: { CALL(17); } break; \
+    case 18: { CALL(18); } break; \
+    case 19: { CALL(19); } break; \
+    case 20: { CALL(20); } break; \
+    case 21: { CALL(21); } break; \
+    case 22: { CALL(22); } break; \
+    case 23: { CALL(23); } break; \
+    case 24: { CALL(24); } break; \
+    case 25: { CALL(25); } break; \
+    case 26: { CALL(26); } break; \
+    case 27: { CALL(27); } break; \
+    case 28: { CALL(28); } break; \
+    case 29: { CALL(29); } break; \
+    case 30: { CALL(30); } break; \
+    case 31: { CALL(31); } break; \
+    case 32: { CALL(32); } break; \
+    default: return dkb_fail(DKB_E_UNSUPPORTED, "block size ns=%d out of range 2..32", ns); \
     }
 
 // x = in - savr (savr may be null); solve; out = x * (wscale*wt) (wt may be null); slot >= 0: sum out^2

@@ -288,21 +288,28 @@ static int grp_grid(i64 npts, int G, int block, int per_sm)
     return (int)g;
 }
 
-#define WEB_DISPATCH(ns, CALL)                                                              \
-    switch (ns) {                                                                           \
-    case 2: { CALL(2); } break;                                                             \
-    case 4: { CALL(4); } break;                                                             \
-    case 6: { CALL(6); } break;                                                             \
-    case 8: { CALL(8); } break;                                                             \
-    case 10: { CALL(10); } break;                                                           \
-    case 12: { CALL(12); } break;                                                           \
-    case 16: { CALL(16); } break;                                                           \
-    case 20: { CALL(20); } break;                                                           \
-    case 24: { CALL(24); } break;                                                           \
-    case 32: { CALL(32); } break;                                                           \
-    default:                                                                                \
-        fprintf(stderr, "daskr_b200: food-web ns=%d not instantiated\n", ns);               \
-        abort();                                                                            \
+// ns = 2*np: every even block size up to 32
+#define WEB_DISPATCH(ns, CALL) \
+    switch (ns) { \
+    case 2: { CALL(2); } break; \
+    case 4: { CALL(4); } break; \
+    case 6: { CALL(6); } break; \
+    case 8: { CALL(8); } break; \
+    case 10: { CALL(10); } break; \
+    case 12: { CALL(12); } break; \
+    case 14: { CALL(14); } break; \
+    case 16: { CALL(16); } break; \
+    case 18: { CALL(18); } break; \
+    case 20: { CALL(20); } break; \
+    case 22: { CALL(22); } break; \
+    case 24: { CALL(24); } break; \
+    case 26: { CALL(26); } break; \
+    case 28: { CALL(28); } break; \
+    case 30: { CALL(30); } break; \
+    case 32: { CALL(32); } break; \
+    default: \
+        fprintf(stderr, "daskr_b200: food-web ns=%d out of range (even, 2..32)\n", ns); \
+        abort(); \
     }
 
 template <int NS, bool DATV>

@@ -113,3 +113,18 @@ def test_solve_web_ns20_spatial_factor(dk, oracle):
     w = 1.0 / (1e-5 * np.abs(o["y"]) + 1e-5)
     assert np.sqrt(np.mean(((g["y"] - o["y"]) * w) ** 2, axis=1)).max() <= 10.0
     assert np.abs(g["counters"][-1][[10, 19]].astype(int) - o["counters"][-1][[10, 19]].astype(int)).max() <= 3
+
+
+@pytest.mark.parametrize("np_,mx,my,jpre", [(3, 16, 12, 3), (7, 12, 10, 3), (9, 32, 8, 3), (11, 10, 9, 1), (13, 9, 8, 3), (15, 8, 8, 1)])
+def test_solve_web_any_block_size(dk, oracle, np_, mx, my, jpre):
+    """The reference takes any ns (src/daskr_rbdpre.f90:102-156); so do residual, block Jacobian + LU, block solve and
+    the Gauss-Seidel factor here (every ns = 2*np up to 32 is instantiated)."""
+    touts = [1e-7, 1e-5, 1e-3]
+    g = dk.solve_web(np_, mx, my, touts, jpre=jpre)
+    o = oracle.run_web(np_, mx, my, touts, jpre=jpre)
+    assert g["idid"] == o["idid"] == 3
+    w = 1.0 / (1e-5 * np.abs(o["y"]) + 1e-5)
+    err = np.sqrt(np.mean(((g["y"] - o["y"]) * w) ** 2, axis=1))
+    print("np=%d %dx%d jpre=%d: wrms(diff)/tol %s; NST/NLI gpu %s cpu %s" % (np_, mx, my, jpre, err, g["counters"][-1][[10, 19]], o["counters"][-1][[10, 19]]))
+    assert err.max() <= 10.0
+    assert np.abs(g["counters"][-1][[10, 19]].astype(int) - o["counters"][-1][[10, 19]].astype(int)).max() <= 3

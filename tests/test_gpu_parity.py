@@ -12,7 +12,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-NS_LIST = [1, 2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32]
+NS_LIST = list(range(1, 33))   # every block size up to one warp per block (the reference takes any ns)
 
 
 def wrms(diff, yref, rtol, atol):
@@ -79,7 +79,8 @@ def _web_setup_gpu(dk, np_, mx, my):
 
 
 @pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (1, 7, 5), (2, 9, 6), (4, 12, 10), (10, 16, 12), (16, 6, 5),
-                                       (1, 32, 9), (10, 64, 13), (5, 32, 32), (8, 96, 7)])   # mx % 32 == 0: staged single-kernel residual
+                                       (1, 32, 9), (10, 64, 13), (5, 32, 32), (8, 96, 7),    # mx % 32 == 0: staged single-kernel residual
+                                       (3, 9, 7), (7, 32, 5), (9, 11, 6), (11, 64, 4), (13, 6, 6), (15, 33, 3)])   # every even ns
 def test_web_res_bit_exact(dk, oracle, np_, mx, my):
     from daskr_b200.api import DeviceBuffer, _ref
 
@@ -93,7 +94,8 @@ def test_web_res_bit_exact(dk, oracle, np_, mx, my):
     assert np.array_equal(d_g, d_o), "max abs diff %.3e" % np.max(np.abs(d_g - d_o))
 
 
-@pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (2, 9, 6), (10, 16, 12), (16, 6, 5)])
+@pytest.mark.parametrize("np_,mx,my", [(1, 20, 20), (2, 9, 6), (10, 16, 12), (16, 6, 5),
+                                       (3, 8, 5), (5, 33, 4), (7, 9, 6), (9, 32, 3), (11, 6, 5), (13, 7, 4), (14, 5, 5), (15, 6, 3)])
 def test_web_jac_psol_bit_exact(dk, oracle, np_, mx, my):
     from daskr_b200.api import DeviceBuffer, _ref
 
