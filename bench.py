@@ -561,6 +561,8 @@ def main():
     ap.add_argument("--cpu-native", action="store_true",
                     help="--impl reference only: also time a -O3 -march=native rebuild of the oracle (courtesy number)")
     ap.add_argument("--cpu-mesh", type=int, default=None)
+    ap.add_argument("--heat-atol", type=float, default=1e-7, help="--workload heat: absolute tolerance (see tools/bench_extra.py)")
+    ap.add_argument("--lu-full", action="store_true", help="--workload lu: include the 1e7-block entries (up to 82 GB of blocks)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: W >= 3 warm-up steps are required for a valid number; got %d" % args.warmup)

@@ -454,11 +454,18 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
 {
     DkbCtx *c = g_ctx;
     ProfScope ps(PROF_GS);
-    // Default: all five iterations in one streaming pass (gs_stream.cu).  DKB_GS_STREAM=0 keeps the five-pass tile
-    // scheduler below (A/B runs, cross-check in the tests).
+    // Two kernels.  gs_stream.cu makes ONE pass over the slab with all five iterations fused (16 bytes per unknown); its
+    // warps form a pipeline across the mx/32 column strips, which takes ~50 rows per strip to fill.  The five-pass tile
+    // scheduler below moves 160 bytes per unknown but has no such start-up.  Measured on B200 at mx = 4096, ns = 20
+    // (profiles/README.md): 544 rows 2.9 vs 2.1 ms, 1056 rows 3.3 vs 3.6 ms, 4096 rows 6.7 vs 14.3 ms -- so short, wide
+    // slabs (8 GPUs on the 4096^2 mesh) keep the tile scheduler.  DKB_GS_STREAM = 0 / 1 forces one of them (tests, A/B runs).
     {
         const char *st_env = getenv("DKB_GS_STREAM");
-        if (!(st_env && atoi(st_env) == 0)) return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z);
+        const int ns0 = c->web.ns;
+        const bool tiles_ok = ns0 == 2 || ns0 == 4 || ns0 == 6 || ns0 == 8 || ns0 == 10 || ns0 == 12 || ns0 == 16 || ns0 == 20 || ns0 == 24 || ns0 == 32;
+        bool stream = !tiles_ok || 5 * (i64)my >= (i64)c->web.mx;
+        if (st_env) stream = atoi(st_env) != 0 || !tiles_ok;
+        if (stream) return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z);
     }
     const WebPar &wp = c->web;
     GsArgs a;

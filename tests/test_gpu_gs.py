@@ -39,7 +39,12 @@ def _gpu_psol(dk, np_, mx, my, jpre, cj, b, lu=None):
                                        (1, 28, 9), (1, 29, 9), (2, 31, 3), (2, 36, 2), (1, 60, 1), (5, 61, 140), (1, 1, 40),
                                        (1, 2, 2), (4, 96, 33), (7, 65, 17), (10, 300, 50), (1, 128, 700)])
 @pytest.mark.parametrize("cj", [1e8, 2.5e3, 7.0])
-def test_gauss_seidel_bit_exact(dk, oracle, np_, mx, my, cj):
+@pytest.mark.parametrize("kernel", ["auto", "stream"])
+def test_gauss_seidel_bit_exact(dk, oracle, np_, mx, my, cj, kernel, monkeypatch):
+    """kernel = auto: the library picks the one-pass streaming kernel or the five-pass tile scheduler by slab shape;
+    stream: the one-pass kernel on every shape (DKB_GS_STREAM=1).  The tile scheduler alone: test below."""
+    if kernel == "stream":
+        monkeypatch.setenv("DKB_GS_STREAM", "1")
     ns = 2 * np_
     rng = np.random.default_rng(mx * 1000 + my + np_)
     b = rng.standard_normal(ns * mx * my)
