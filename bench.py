@@ -476,6 +476,7 @@ def run_web_bench(args, out_fd):
     cdot[:] = d_yp_ic.cpu().numpy()
     del d_y_ic, d_yp_ic
     dk.set_option(dk.OPT_MAX_STEPS, 500)
+    dk.set_option(dk.OPT_ASYNC_OUT, 0 if args.sync_out else 1)
     barrier()
     ei0, ei1 = events()
     ei0.record(stream)
@@ -497,16 +498,20 @@ def run_web_bench(args, out_fd):
         tcur, idid = dk.daskr(dk.WEB_RES, neq, tcur, c, cdot, TOUT, info, RTOL, ATOL, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
         if idid < 0:
             raise SystemExit("e2e window failed idid=%d" % idid)
+    dk.output_wait()   # the last step's y / yprime have arrived in the pinned host arrays
     e1.record(stream)
     barrier()
+    dk.set_option(dk.OPT_ASYNC_OUT, 0)
     ms_e2e = maxrank(e0.elapsed_time(e1))
     dnli_e2e = int(iwork[19]) - nli0
     hdr_bytes = 60 * 8 + 40 * 4 + 20 * 4 + 5 * 8
     e2e = {"value": dnli_e2e / (ms_e2e * 1e-3), "unit": "it/s", "h2d_bytes_per_step": hdr_bytes, "d2h_bytes_per_step": 16 * neq,
            "h2d_bytes_initial": 16 * neq, "initial_call_ms": initial_call_ms, "ms_per_step": ms_e2e / K, "nli": dnli_e2e,
            "bytes_are": "per GPU (each rank copies its slab)",
-           "mode": "pinned host y/yprime, info(3)=1: one dkb_daskr call per step, y+yprime D2H at every return; "
-                   "y/yprime are inputs only on the initial call (DASKR convention), so per-step H2D is the scalar headers"}
+           "mode": "pinned host y/yprime, info(3)=1: one dkb_daskr call per step, y+yprime D2H at every return%s; "
+                   "y/yprime are inputs only on the initial call (DASKR convention), so per-step H2D is the scalar headers"
+                   % ("" if args.sync_out else " (DKB_OPT_ASYNC_OUT: the transfer of step n runs on a second stream under step n+1; "
+                                               "the window ends when the last transfer has arrived)")}
     log("[rank %d] e2e: %d steps in %.1f ms, dNLI=%d" % (rank, K, ms_e2e, dnli_e2e))
 
     # =========== (3) CPU baseline (rank 0, N=1 only) ===========
@@ -558,6 +563,7 @@ def main():
     ap.add_argument("--steps2", type=int, default=6)
     ap.add_argument("--warmup2", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sync-out", action="store_true", help="e2e leg: blocking y/yprime transfer at every return (no DKB_OPT_ASYNC_OUT)")
     ap.add_argument("--cpu-native", action="store_true",
                     help="--impl reference only: also time a -O3 -march=native rebuild of the oracle (courtesy number)")
     ap.add_argument("--cpu-mesh", type=int, default=None)

@@ -48,6 +48,8 @@ from .api import (  # noqa: F401
     OPT_DEVICE_IO,
     OPT_FUSED,
     OPT_MAX_STEPS,
+    OPT_ASYNC_OUT,
+    output_wait,
 )
 
 __version__ = "0.1.0"

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_lib", "libdaskr_b200.so")
 
-OPT_DEVICE_IO, OPT_FUSED, OPT_MAX_STEPS = 1, 2, 3
+OPT_DEVICE_IO, OPT_FUSED, OPT_MAX_STEPS, OPT_ASYNC_OUT = 1, 2, 3, 4
 
 
 class DaskrError(RuntimeError):
@@ -27,7 +27,7 @@ PSOL_T = C.CFUNCTYPE(None, *([C.c_void_p] * 15))
 
 # every symbol include/daskr_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "dkb_init", "dkb_finalize", "dkb_last_error", "dkb_version", "dkb_stream", "dkb_set_option", "dkb_sync",
+    "dkb_init", "dkb_finalize", "dkb_last_error", "dkb_version", "dkb_stream", "dkb_set_option", "dkb_sync", "dkb_output_wait",
     "dkb_comm_unique_id", "dkb_comm_init", "dkb_setup_rbdpre", "dkb_setup_rbgpre", "dkb_slab", "dkb_web_setpar", "dkb_web_setpar_ex",
     "dkb_web_res",
     "dkb_web_jac", "dkb_web_psol", "dkb_web_cinit", "dkb_heat_setpar", "dkb_heat_res", "dkb_heat_jac",
@@ -156,6 +156,11 @@ def state_export():
 def state_import(buf):
     buf = np.ascontiguousarray(buf, dtype=np.uint8)
     _check(lib().dkb_state_import(_p(buf), buf.size), "dkb_state_import")
+
+
+def output_wait():
+    """OPT_ASYNC_OUT: block until the y / yprime of the last return have arrived in the caller's (pinned) arrays."""
+    _check(lib().dkb_output_wait(), "dkb_output_wait")
 
 
 def set_option(opt, value):

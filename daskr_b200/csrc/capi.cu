@@ -37,13 +37,14 @@ void dkb_cuda_check(const char *what)
 // use never needs the library; with torch in the process this binds to the copy torch loaded)
 typedef struct { char internal[128]; } nccl_uid;
 typedef void *nccl_comm;
-enum { NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
+enum { NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2, NCCL_MIN = 3 };
 static struct {
     void *lib;
     int (*GetUniqueId)(nccl_uid *);
     int (*CommInitRank)(nccl_comm *, int, nccl_uid, int);
     int (*CommDestroy)(nccl_comm);
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t);
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t);
     int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t);
     int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t);
     int (*GroupStart)(void);
@@ -64,6 +65,7 @@ static int nccl_load()
     SYM(CommInitRank);
     SYM(CommDestroy);
     SYM(AllReduce);
+    SYM(AllGather);
     SYM(Send);
     SYM(Recv);
     SYM(GroupStart);
@@ -99,12 +101,222 @@ void allreduce_min_int(int *d_val, int count)
     nccl_check(N.AllReduce(d_val, d_val, count, NCCL_INT32, NCCL_MIN, c->comm, c->stream), "allreduce_min_int");
 }
 
+// ---------------------------------------------------------------- peer memory (CUDA IPC over NVLink / NVSwitch)
+// All-gather of one fixed-size record per rank through NCCL (set-up only), host in / host out.
+static int gather_records(const void *mine, void *all, size_t bytes)
+{
+    DkbCtx *c = g_ctx;
+    char *d = nullptr;
+    if (cudaMalloc(&d, bytes * (c->nranks + 1)) != cudaSuccess) return dkb_fail(DKB_E_CUDA, "peer set-up: cudaMalloc failed");
+    cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, c->stream);
+    int e = N.AllGather(d, d + bytes, bytes, NCCL_INT8, c->comm, c->stream);
+    cudaMemcpyAsync(all, d + bytes, bytes * c->nranks, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != 0) return dkb_fail(DKB_E_NCCL, "ncclAllGather: %s", N.GetErrorString(e));
+    return 0;
+}
+
+struct PeerRecord {
+    cudaIpcMemHandle_t h;
+    long long words;     // size of the allocation in doubles (the arenas must agree for the halo path)
+    int ok;              // the rank could export its buffer
+    int pad;
+};
+
+// Map one buffer of every rank into this process.  Returns 0 and fills out[] only if every rank succeeded
+// (`same_size`: and all sizes agree) -- the decision is identical on all ranks because it is made on the gathered table.
+static int peer_map(double *mine, long long words, bool same_size, double **out, const char *what)
+{
+    DkbCtx *c = g_ctx;
+    PeerRecord me;
+    memset(&me, 0, sizeof me);
+    me.words = words;
+    me.ok = (mine != nullptr && cudaIpcGetMemHandle(&me.h, mine) == cudaSuccess) ? 1 : 0;
+    cudaGetLastError();
+    std::vector<PeerRecord> all(c->nranks);
+    if (gather_records(&me, all.data(), sizeof me) != 0) return -1;
+    bool ok = true;
+    for (int r = 0; r < c->nranks; ++r) ok = ok && all[r].ok && (!same_size || all[r].words == words);
+    int opened = 0;
+    if (ok) {
+        for (int r = 0; r < c->nranks && ok; ++r) {
+            if (r == c->rank) {
+                out[r] = mine;
+                continue;
+            }
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+            } else {
+                out[r] = (double *)p;
+                ++opened;
+            }
+        }
+    }
+    // every rank must agree on the outcome: a rank that could not open a peer turns the path off for all
+    double flag = ok ? 0.0 : 1.0;
+    cudaMemcpyAsync(c->d_scal + 50, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    allreduce_max(50, 1);
+    cudaMemcpyAsync(&flag, c->d_scal + 50, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (flag != 0.0) {
+        for (int r = 0; r < c->nranks; ++r) {
+            if (r != c->rank && out[r] && ok) cudaIpcCloseMemHandle(out[r]);
+            out[r] = nullptr;
+        }
+        if (getenv("DKB_PEER_VERBOSE")) fprintf(stderr, "daskr_b200[%d]: peer mapping of %s not available, NCCL path stays\n", c->rank, what);
+        return 1;
+    }
+    (void)opened;
+    return 0;
+}
+
+static void peer_unmap(double **tab)
+{
+    DkbCtx *c = g_ctx;
+    for (int r = 0; r < DKB_PEER_MAX; ++r) {
+        if (tab[r] && r != c->rank) cudaIpcCloseMemHandle(tab[r]);
+        tab[r] = nullptr;
+    }
+}
+
+// called from dkb_comm_init: the mailboxes
+static void peer_setup_mailboxes()
+{
+    DkbCtx *c = g_ctx;
+    c->peer_ok = 0;
+    const char *env = getenv("DKB_PEER");
+    if (c->nranks <= 1 || c->nranks > DKB_PEER_MAX || (env && atoi(env) == 0)) return;
+    if (cudaMalloc(&c->my_box, sizeof(double) * DKB_BOX_WORDS) != cudaSuccess) return;
+    cudaMemset(c->my_box, 0, sizeof(double) * DKB_BOX_WORDS);
+    if (!c->halo_ticket) {
+        cudaMalloc(&c->halo_ticket, sizeof(unsigned));
+        cudaMemset(c->halo_ticket, 0, sizeof(unsigned));
+    }
+    if (peer_map(c->my_box, DKB_BOX_WORDS, true, c->peer_box, "mailboxes") == 0) c->peer_ok = 1;
+    c->ar_seq = c->halo_seq = 0;
+}
+
+// called after alloc_solver (re)allocated the arena: collective over all ranks
+int peer_map_arena()
+{
+    DkbCtx *c = g_ctx;
+    if (c->peer_arena_ok) peer_unmap(c->peer_arena);
+    c->peer_arena_ok = 0;
+    if (!c->peer_ok) return 0;
+    if (peer_map(c->arena, c->arena_doubles, true, c->peer_arena, "solver arenas") == 0) c->peer_arena_ok = 1;
+    return 0;
+}
+
+PeerComm peer_comm_next()
+{
+    DkbCtx *c = g_ctx;
+    PeerComm pc;
+    memset(&pc, 0, sizeof pc);
+    pc.nranks = 1;
+    if (c->nranks > 1 && c->peer_ok) {
+        pc.nranks = c->nranks;
+        pc.rank = c->rank;
+        pc.seq = ++c->ar_seq;
+        for (int r = 0; r < c->nranks; ++r) pc.box[r] = c->peer_box[r];
+    }
+    return pc;
+}
+
+// K9 over peer memory: every rank stores its first / last mesh row straight into the halo room of the neighbour's copy
+// of the same vector (same arena layout on every rank), then tells the neighbour and waits for the neighbour's rows.
+struct HaloPut {
+    int nv, has_lo, has_hi;
+    i64 h, n;                          // doubles per mesh row, local vector length
+    i64 off[3];                        // offsets of the vectors in the arena
+    double *mine, *lo, *hi;            // arenas: own, of rank-1, of rank+1
+    double *box_lo, *box_hi, *box_me;  // mailboxes
+    unsigned long long seq;
+    unsigned *ticket;
+};
+__global__ void __launch_bounds__(256) halo_put_kernel(const HaloPut p)
+{
+    __shared__ int is_last;
+    const i64 per = p.h;               // h is even whenever ns is even; odd lengths go one double at a time
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (int k = 0; k < p.nv; ++k) {
+        const double *v = p.mine + p.off[k];
+        if ((per & 1) == 0) {
+            const i64 n2 = per / 2;
+            for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+                if (p.has_lo) reinterpret_cast<double2 *>(p.lo + p.off[k] + p.n)[i] = reinterpret_cast<const double2 *>(v)[i];
+                if (p.has_hi) reinterpret_cast<double2 *>(p.hi + p.off[k] - per)[i] = reinterpret_cast<const double2 *>(v + p.n - per)[i];
+            }
+        } else {
+            for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += stride) {
+                if (p.has_lo) p.lo[p.off[k] + p.n + i] = v[i];
+                if (p.has_hi) p.hi[p.off[k] - per + i] = v[p.n - per + i];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicInc(p.ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        // my first row sits in the lower neighbour's room ABOVE its slab, my last row in the upper neighbour's room BELOW
+        if (p.has_lo) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"((unsigned long long *)(p.box_lo + DKB_BOX_HFLAG) + 1), "l"(p.seq) : "memory");
+        if (p.has_hi) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"((unsigned long long *)(p.box_hi + DKB_BOX_HFLAG) + 0), "l"(p.seq) : "memory");
+        unsigned long long vflag;
+        if (p.has_lo) {
+            const unsigned long long *f = (const unsigned long long *)(p.box_me + DKB_BOX_HFLAG) + 0;   // rows from below
+            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(vflag) : "l"(f) : "memory"); } while (vflag < p.seq);
+        }
+        if (p.has_hi) {
+            const unsigned long long *f = (const unsigned long long *)(p.box_me + DKB_BOX_HFLAG) + 1;   // rows from above
+            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(vflag) : "l"(f) : "memory"); } while (vflag < p.seq);
+        }
+    }
+}
+
+static bool halo_exchange_peer(double *const *vecs, int nv)
+{
+    DkbCtx *c = g_ctx;
+    if (!c->peer_arena_ok || nv > 3) return false;
+    HaloPut p;
+    memset(&p, 0, sizeof p);
+    for (int k = 0; k < nv; ++k) {
+        if (vecs[k] < c->arena || vecs[k] >= c->arena + c->arena_doubles) return false;   // only the solver's own vectors have twins
+        p.off[k] = vecs[k] - c->arena;
+    }
+    p.nv = nv;
+    p.has_lo = c->rank > 0;
+    p.has_hi = c->rank < c->nranks - 1;
+    p.h = c->halo;
+    p.n = c->neq;
+    p.mine = c->arena;
+    p.lo = p.has_lo ? c->peer_arena[c->rank - 1] : nullptr;
+    p.hi = p.has_hi ? c->peer_arena[c->rank + 1] : nullptr;
+    p.box_me = c->my_box;
+    p.box_lo = p.has_lo ? c->peer_box[c->rank - 1] : nullptr;
+    p.box_hi = p.has_hi ? c->peer_box[c->rank + 1] : nullptr;
+    p.seq = ++c->halo_seq;
+    p.ticket = c->halo_ticket;
+    const int grid = (int)std::min<i64>(std::max<i64>((c->halo / 2 + 255) / 256, 1), 64);
+    halo_put_kernel<<<grid, 256, 0, c->stream>>>(p);
+    COUNT_LAUNCH();
+    return true;
+}
+
 // K9: one mesh row to each slab neighbour (ghost row of the lower neighbour's top, and v.v.)
 static void halo_exchange_n(double *const *vecs, int nv)
 {
     DkbCtx *c = g_ctx;
     if (c->nranks <= 1) return;
     ProfScope ps(PROF_HALO);
+    if (halo_exchange_peer(vecs, nv)) return;
     const i64 h = c->halo, n = c->neq;
     nccl_check(N.GroupStart(), "halo group");
     for (int k = 0; k < nv; ++k) {
@@ -237,7 +449,19 @@ int dkb_finalize(void)
     DkbCtx *c = g_ctx;
     if (!c) return 0;
     cudaStreamSynchronize(c->stream);
+    if (c->peer_arena_ok) peer_unmap(c->peer_arena);
+    if (c->peer_ok) peer_unmap(c->peer_box);
+    cudaFree(c->my_box);
+    cudaFree(c->halo_ticket);
     if (c->comm && N.CommDestroy) N.CommDestroy(c->comm);
+    if (c->out_stream) {
+        cudaStreamSynchronize(c->out_stream);
+        cudaStreamDestroy(c->out_stream);
+        cudaEventDestroy(c->ev_snap);
+        cudaEventDestroy(c->ev_out);
+    }
+    cudaFree(c->out_y);
+    cudaFree(c->out_yp);
     cudaFree(c->arena);
     cudaFree(c->wp);
     cudaFree(c->iwp);
@@ -284,6 +508,7 @@ int dkb_set_option(int opt, int64_t value)
     case DKB_OPT_DEVICE_IO: g_ctx->opt_device_io = value != 0; break;
     case DKB_OPT_FUSED: g_ctx->opt_fused = (int)value; break;   // 0 callbacks, 1 two kernels, 2 single kernel
     case DKB_OPT_MAX_STEPS: g_ctx->opt_max_steps = value > 0 ? value : 500; break;
+    case DKB_OPT_ASYNC_OUT: g_ctx->opt_async_out = value != 0; break;
     case 99: g_ctx->debug_variant = (int)value; break;   // kernel-variant selector for tuning runs (not in the header)
     default: return dkb_fail(DKB_E_ARG, "unknown option %d", opt);
     }
@@ -320,6 +545,7 @@ int dkb_comm_init(const void *id128, int rank, int nranks)
     c->comm = comm;
     c->rank = rank;
     c->nranks = nranks;
+    peer_setup_mailboxes();   // collective: scalar all-reductions and halo rows go through peer memory when the node allows it
     return 0;
 }
 

@@ -45,6 +45,21 @@ struct ProfSlot {
 enum { PROF_DATV = 0, PROF_MGS, PROF_PSOL0, PROF_JAC, PROF_RES, PROF_VEC, PROF_NORM, PROF_HALO, PROF_TPP, PROF_RESDATV, PROF_DATV1, PROF_KIT, PROF_GS,
        PROF_NSLOTS };
 
+// ---------------------------------------------------------------- peer memory (one node, NVLink / NVSwitch)
+// Every rank owns a small mailbox in its HBM that all ranks of the node map (CUDA IPC).  Scalar all-reductions and the
+// one-row halo exchange write straight into the peers' memory from inside the kernels that produce the data -- no NCCL
+// call, no extra launch -- and spin on flags in their own mailbox (capi.cu: peer_*; vecops.cu: reduce_kernel's last block).
+#define DKB_PEER_MAX 8
+#define DKB_BOX_VAL 0          // doubles [2 parities][DKB_PEER_MAX sources][8 components]
+#define DKB_BOX_ARFLAG 128     // u64 [DKB_PEER_MAX sources]: sequence number of the source's latest contribution
+#define DKB_BOX_HFLAG 136      // u64 [2]: halo rows arrived from below / from above (sequence numbers)
+#define DKB_BOX_WORDS 256
+struct PeerComm {
+    int nranks, rank;                  // nranks <= 1: no exchange
+    unsigned long long seq;            // this all-reduction's sequence number (same on every rank)
+    double *box[DKB_PEER_MAX];         // box[r]: rank r's mailbox as mapped in this process (box[rank]: own)
+};
+
 // ---------------------------------------------------------------- context
 struct DkbCtx {
     int device = 0;
@@ -55,11 +70,25 @@ struct DkbCtx {
     int opt_device_io = 0;
     int opt_fused = 2;           // 0: datv through the callbacks, 1: residual + solve kernels, 2: single fused kernel
     i64 opt_max_steps = 500;
+    int opt_async_out = 0;       // DKB_OPT_ASYNC_OUT: y / yprime returned through a snapshot + second stream (driver.cu)
+    cudaStream_t out_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_out = nullptr;
+    double *out_y = nullptr, *out_yp = nullptr;
+    i64 out_cap = 0;
+    int out_pending = 0;
     int debug_variant = 0;       // kernel-variant selector for tuning runs (dkb_debug_*)
 
     // communicator (NCCL, loaded lazily)
     int rank = 0, nranks = 1;
     void *comm = nullptr;
+    // peer-memory path (all ranks on one node, equal slabs): mailboxes and the solver arenas of all ranks, mapped here
+    int peer_ok = 0;                     // mailboxes mapped
+    int peer_arena_ok = 0;               // arenas of the slab neighbours mapped (same layout on every rank)
+    double *peer_box[DKB_PEER_MAX] = {nullptr};
+    double *peer_arena[DKB_PEER_MAX] = {nullptr};
+    double *my_box = nullptr;
+    unsigned long long ar_seq = 0, halo_seq = 0;
+    unsigned *halo_ticket = nullptr;
 
     // mesh (setup_rbdpre): mx, global my, local slab
     int rbd_set = 0;
@@ -211,6 +240,8 @@ double r_nrm2(i64 n, const double *x);
 void allreduce_sum(int slot, int count);
 void allreduce_max(int slot, int count);
 void allreduce_min_int(int *d_val, int count);
+PeerComm peer_comm_next();        // capi.cu: descriptor of the next in-kernel all-reduction (nranks = 1 if the peer path is off)
+int peer_map_arena();             // capi.cu: (re)map the neighbours' solver arenas after alloc_solver (collective)
 
 // ---------------------------------------------------------------- LU (lu.cu)
 int lu_dgefa_batched(double *bd, int *ipbd, int ns, i64 nblk, int *info, int *d_first_flag);

@@ -112,6 +112,69 @@ __global__ void __launch_bounds__(256) heat_datv_kernel(HeatDev h, i64 n, const 
     }
 }
 
+
+// The same in tiles (default): CTA = 256 columns x HT_TY rows.  The perturbed state z = y + v/wght of the tile and its
+// one-point halo goes to shared memory once (one divide per point instead of five: each neighbour's z is otherwise
+// re-formed from y, v, wt), then every thread walks its column.  Statement for statement the arithmetic of datv:3493-3518
+// with res:72-87 and the 1x1 dgesl inlined, so the result is bit-identical to heat_datv_kernel.
+#define HT_TX 256
+#define HT_TY 8
+__global__ void __launch_bounds__(HT_TX) heat_datv_tile_kernel(HeatDev h, const double *__restrict__ v, double vscale,
+                                                             const double *__restrict__ wt, double wscale,
+                                                             const double *__restrict__ y, const double *__restrict__ ydot,
+                                                             const double *__restrict__ savr, double cj,
+                                                             const double *__restrict__ bd, double *__restrict__ vnext)
+{
+    __shared__ double Z[HT_TY + 2][HT_TX + 2];
+    const int tid = threadIdx.x;
+    const int tiles_x = (h.m2 + HT_TX - 1) / HT_TX;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * HT_TX, y0 = ty * HT_TY;
+    const int x = x0 + tid;
+    const int xc = min(x, h.m2 - 1);
+    // rows y0-1 .. y0+HT_TY of this thread's column (rows -1 / my are the slab halo rows every solver vector carries)
+    double wg[HT_TY], vt[HT_TY];
+#pragma unroll
+    for (int r = 0; r < HT_TY + 2; ++r) {
+        const int yy = min(y0 + r - 1, h.my);
+        const i64 g = (i64)yy * h.m2 + xc;
+        const double w = wscale * __ldg(wt + g);
+        const double t = (vscale * __ldg(v + g)) / w;          // vtemp = v/wght
+        Z[r][tid + 1] = __ldg(y + g) + t;                       // z = y + vtemp
+        if (r >= 1 && r <= HT_TY) {
+            wg[r - 1] = w;
+            vt[r - 1] = t;
+        }
+    }
+    if (tid < 2 * HT_TY) {   // halo columns x0-1 and x0+HT_TX of the HT_TY rows
+        const int r = (tid % HT_TY) + 1, side = tid / HT_TY;
+        const int yy = min(y0 + r - 1, h.my);
+        const int xx = side ? min(x0 + HT_TX, h.m2 - 1) : max(x0 - 1, 0);
+        const i64 g = (i64)yy * h.m2 + xx;
+        Z[r][side ? HT_TX + 1 : 0] = __ldg(y + g) + (vscale * __ldg(v + g)) / (wscale * __ldg(wt + g));
+    }
+    __syncthreads();
+    if (x >= h.m2) return;
+#pragma unroll
+    for (int r = 0; r < HT_TY; ++r) {
+        const int yl = y0 + r;
+        if (yl >= h.my) break;
+        const i64 i = (i64)yl * h.m2 + x;
+        const int k = yl + h.jy0;
+        const double zi = Z[r + 1][tid + 1];
+        double d = zi;                                          // res: delta = u on the boundary
+        if (x >= 1 && x <= h.m2 - 2 && k >= 1 && k <= h.my_g - 2) {
+            const double ydt = __ldg(ydot + i) + vt[r] * cj;    // ydottemp = ydot + vtemp*cj
+            const double temx = Z[r + 1][tid] + Z[r + 1][tid + 2];
+            const double temy = Z[r][tid + 1] + Z[r + 2][tid + 1];
+            d = ydt - (temx + temy - 4 * zi) * h.coeff;
+        }
+        d = d - __ldg(savr + i);
+        d = d / __ldg(bd + i);
+        vnext[i] = d * wg[r];
+    }
+}
+
 static int hgrid(i64 n)
 {
     i64 g = (n + 255) / 256;
@@ -136,7 +199,14 @@ void heat_datv_fused(const double *v, double vscale, const double *wt, double ws
                      const double *savr, double cj, const double *bd, double *vnext)
 {
     DkbCtx *c = g_ctx;
-    heat_datv_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(make_heatdev(cj), c->npts, v, vscale, wt, wscale, y, ydot,
-                                                            savr, cj, bd, vnext);
+    const HeatDev h = make_heatdev(cj);
+    auto in_arena = [&](const double *p) { return c->arena && p >= c->arena && p < c->arena + c->arena_doubles; };
+    // the tiled kernel reads one mesh row before / after the slab: only the solver's own vectors have that room
+    if (c->debug_variant != 8 && in_arena(v) && in_arena(wt) && in_arena(y) && c->halo_pad >= h.m2) {
+        const int tiles = ((h.m2 + HT_TX - 1) / HT_TX) * ((h.my + HT_TY - 1) / HT_TY);
+        heat_datv_tile_kernel<<<tiles, HT_TX, 0, c->stream>>>(h, v, vscale, wt, wscale, y, ydot, savr, cj, bd, vnext);
+    } else {
+        heat_datv_kernel<<<hgrid(c->npts), 256, 0, c->stream>>>(h, c->npts, v, vscale, wt, wscale, y, ydot, savr, cj, bd, vnext);
+    }
     COUNT_LAUNCH();
 }

@@ -329,12 +329,19 @@ __device__ __forceinline__ void block_reduce(double (&acc)[KS + KM], double *sh)
     __syncthreads();
 }
 
+// Several ranks (pc.nranks > 1): the block that finishes last also performs the all-reduction, through peer memory.
+// It stores this rank's K totals into every rank's mailbox (NVLink stores, one thread per destination), publishes them
+// with a sequence number, waits for the same sequence number from every source in its own mailbox and combines the
+// P contributions in rank order -- the same order on every rank, so all ranks hold bit-identical results (which the
+// replicated host control relies on).  Values are double-buffered by the parity of the sequence number: a rank can be
+// at most one all-reduction ahead of the slowest one, because every all-reduction needs everybody's contribution.
 template <int KS, int KM, class F>
 __global__ void __launch_bounds__(DKB_RED_BLOCK) reduce_kernel(F f, i64 n, double *part,
-                                                               unsigned *ticket, double *out)
+                                                               unsigned *ticket, double *out, const PeerComm pc)
 {
     constexpr int K = KS + KM;
     __shared__ double sh[(DKB_RED_BLOCK / 32) * K];
+    __shared__ double tot[K];
     __shared__ int is_last;
     double acc[K];
 #pragma unroll
@@ -365,20 +372,61 @@ __global__ void __launch_bounds__(DKB_RED_BLOCK) reduce_kernel(F f, i64 n, doubl
             }
         }
         block_reduce<KS, KM>(acc, sh);
+        if (pc.nranks <= 1) {
+            if (threadIdx.x == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) out[k] = acc[k];
+            }
+            return;
+        }
         if (threadIdx.x == 0) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) out[k] = acc[k];
+            for (int k = 0; k < K; ++k) tot[k] = acc[k];
+        }
+        __syncthreads();
+        const int par = (int)(pc.seq & 1ull);
+        if ((int)threadIdx.x < pc.nranks) {
+            const int r = threadIdx.x;
+            double *dst = pc.box[r] + DKB_BOX_VAL + (par * DKB_PEER_MAX + pc.rank) * 8;
+#pragma unroll
+            for (int k = 0; k < K; ++k) dst[k] = tot[k];
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"((unsigned long long *)(pc.box[r] + DKB_BOX_ARFLAG) + pc.rank), "l"(pc.seq) : "memory");
+            // ... and wait for source r's contribution in this rank's own mailbox
+            const unsigned long long *fl = (const unsigned long long *)(pc.box[pc.rank] + DKB_BOX_ARFLAG) + r;
+            unsigned long long seen;
+            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(fl) : "memory"); } while (seen < pc.seq);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const volatile double *src = pc.box[pc.rank] + DKB_BOX_VAL + par * DKB_PEER_MAX * 8;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double t = (k < KS) ? 0.0 : -DBL_MAX;
+                for (int r = 0; r < pc.nranks; ++r) {
+                    const double v = src[r * 8 + k];
+                    t = (k < KS) ? (t + v) : fmax(t, v);
+                }
+                out[k] = t;
+            }
         }
     }
 }
 
+// One launch: local reduction + (several ranks) the all-reduction of the KS sums and KM maxima -- inside the kernel when
+// the peer-memory path is up, by NCCL calls behind it otherwise.
 template <int KS, int KM, class F>
 static void launch_reduce(F f, i64 n, int slot)
 {
     DkbCtx *c = g_ctx;
+    const PeerComm pc = peer_comm_next();
     reduce_kernel<KS, KM, F><<<red_grid(n), DKB_RED_BLOCK, 0, c->stream>>>(f, n, c->d_part, c->d_ticket,
-                                                                            c->d_scal + slot);
+                                                                            c->d_scal + slot, pc);
     COUNT_LAUNCH();
+    if (c->nranks > 1 && pc.nranks <= 1) {
+        if (KS > 0) allreduce_sum(slot, KS);
+        if (KM > 0) allreduce_max(slot + KS, KM);
+    }
 }
 
 struct RDot {
@@ -466,12 +514,10 @@ struct RMaxVal {
 void r_sum_strided(i64 npts, i64 stride, i64 off, const double *x, int slot)
 {
     launch_reduce<1, 0>(RSumStrided{x, stride, off}, npts, slot);
-    allreduce_sum(slot, 1);
 }
 void r_max(i64 n, const double *x, int slot)
 {
     launch_reduce<0, 1>(RMaxVal{x}, n, slot);
-    allreduce_max(slot, 1);
 }
 // dcnstr, src/daskr_new.f90:569-661, as one reduction.  The reference scans the unknowns in order, returns at the first
 // hard violation (tau = 0.6*tau) and otherwise compares the largest relative change rdymx of the |icnstr| = 2 unknowns
@@ -499,7 +545,6 @@ struct RCnstr {
 void r_cnstr(i64 n, const double *y, const double *ynew, const int *icnstr, int slot)
 {
     launch_reduce<0, 2>(RCnstr{y, ynew, icnstr}, n, slot);   // [rdymx, hard-violation flag], both maxima (-DBL_MAX if none)
-    allreduce_max(slot, 2);
 }
 
 // dcnst0, src/daskr_new.f90:663-713: is the initial y consistent with the constraints?  flag = smallest violating
@@ -523,33 +568,26 @@ void v_cnst0(i64 n, const double *y, const int *icnstr, int *d_flag)
 void r_dot(i64 n, const double *x, const double *y, int slot)
 {
     launch_reduce<1, 0>(RDot{x, y}, n, slot);
-    allreduce_sum(slot, 1);
 }
 void r_dot_s(i64 n, const double *x, double sx, const double *y, int slot)
 {
     launch_reduce<1, 0>(RDotS{x, y, sx}, n, slot);
-    allreduce_sum(slot, 1);
 }
 void r_dot2(i64 n, const double *vnew, const double *v1, double s1, int slot)
 {
     launch_reduce<2, 0>(RDot2{vnew, v1, s1}, n, slot);
-    allreduce_sum(slot, 2);
 }
 void r_axpy_dot(i64 n, double *vnew, const double *vi, double si, int hslot, const double *vnext, double sn, int slot)
 {
     launch_reduce<1, 0>(RAxpyDot{vnew, vi, g_ctx->d_scal + hslot, vnext, si, sn, 0.0}, n, slot);
-    allreduce_sum(slot, 1);
 }
 void r_axpy_nrm(i64 n, double *vnew, const double *vi, double si, int hslot, int slot)
 {
     launch_reduce<1, 0>(RAxpyNrm{vnew, vi, g_ctx->d_scal + hslot, si, 0.0}, n, slot);
-    allreduce_sum(slot, 1);
 }
 void r_wrms_parts(i64 n, const double *v, const double *rwt, int slot)
 {
     launch_reduce<1, 1>(RWrms{v, rwt}, n, slot);
-    allreduce_sum(slot, 1);
-    allreduce_max(slot + 1, 1);
 }
 
 void scal_fetch(int slot, int count, double *out)
@@ -577,7 +615,6 @@ double r_wrms(i64 n, const double *v, const double *rwt)
     double nn = (double)c->neq_g;
     if (isfinite(sum) && sum > 1e-280) return sqrt(sum / nn);
     launch_reduce<1, 0>(RWrmsScaled{v, rwt, vmax}, n, slot);
-    allreduce_sum(slot, 1);
     scal_fetch(slot, 1, r);
     return vmax * sqrt(r[0] / nn);
 }
@@ -617,8 +654,6 @@ bool r_wrms3(i64 n, int nn, const double *e, const double *rwt, const double *ph
     ProfScope ps(PROF_NORM);
     const int slot = 52;
     launch_reduce<3, 3>(RWrms3{e, rwt, phi_kp1, phi_k, nn}, n, slot);
-    allreduce_sum(slot, 3);
-    allreduce_max(slot + 3, 3);
     double r[6];
     scal_fetch(slot, 6, r);
     const double cnt = (double)c->neq_g;

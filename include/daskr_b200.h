@@ -49,7 +49,10 @@ enum {
 enum {
     DKB_OPT_DEVICE_IO = 1,  /* 1: y/yprime passed to dkb_daskr are device pointers */
     DKB_OPT_FUSED = 2,      /* built-in problems: 2 (default) single-kernel datv, 1 two kernels, 0 plain callbacks */
-    DKB_OPT_MAX_STEPS = 3   /* per-call step limit (reference: 500, src/daskr.f:2057) */
+    DKB_OPT_MAX_STEPS = 3,  /* per-call step limit (reference: 500, src/daskr.f:2057) */
+    DKB_OPT_ASYNC_OUT = 4   /* 1: successful returns hand y / yprime to the host through a device snapshot and a second
+                             * stream, overlapping the PCIe transfer with the next call's step; the arrays (pinned host
+                             * memory) are complete after dkb_output_wait() or after the next dkb_daskr call returns */
 };
 
 /* ---- callback contracts: src/daskr_new.f90:11-21, 35-53, 55-71 ----
@@ -87,6 +90,7 @@ int dkb_version(void);
 void *dkb_stream(void);              /* cudaStream_t the library launches on */
 int dkb_set_option(int opt, int64_t value);
 int dkb_sync(void);
+int dkb_output_wait(void);           /* DKB_OPT_ASYNC_OUT: block until the last returned y / yprime have arrived */
 
 /* ---- multi-GPU: y-slab decomposition, NCCL halo exchange + scalar allreduce ----
  * dkb_comm_unique_id writes an ncclUniqueId (128 bytes) on rank 0; every rank

@@ -139,6 +139,34 @@ def test_tolerances_are_reread_on_continuation(dk, oracle):
     assert g_cnt[10] > 60                             # the tighter tolerance really took effect (the loose run takes ~40 steps)
 
 
+def test_async_output_equals_blocking_output(dk):
+    """DKB_OPT_ASYNC_OUT: y / yprime of every intermediate-output return arrive through a snapshot and a second stream;
+    after dkb_output_wait() they are the bits the blocking transfer delivers."""
+    outs = {}
+    for mode in (0, 1):
+        neq, iwork = _setup(dk)
+        dk.set_option(dk.OPT_ASYNC_OUT, mode)
+        info = np.zeros(20, dtype=np.int32)
+        info[[2, 10, 11, 13, 14, 15]] = 1            # info(3) = 1: return after every step
+        rwork, rpar, ipar = np.zeros(60), np.zeros(1), np.array([3, 0], dtype=np.int32)
+        c, cdot = dk.web_cinit(neq)
+        t, idid = dk.daskr(dk.WEB_RES, neq, 0.0, c, cdot, 1e-3, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
+        info[10] = 0
+        ys = []
+        for _ in range(25):
+            t, idid = dk.daskr(dk.WEB_RES, neq, t, c, cdot, 1e-3, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
+            assert idid in (1, 3)
+            dk.output_wait()
+            ys.append((t, c.copy(), cdot.copy()))
+            if idid == 3:
+                break
+        outs[mode] = ys
+        dk.set_option(dk.OPT_ASYNC_OUT, 0)
+    assert len(outs[0]) == len(outs[1]) > 5
+    for a, b in zip(outs[0], outs[1]):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
 def test_import_rejects_garbage(dk):
     _setup(dk)
     with pytest.raises(dk.DaskrError):
