@@ -262,7 +262,9 @@ int tpp_to_reference(int ns, i64 npts, const double *lut, const int *pt, double 
 void web_upload_tables();
 void web_res_launch(const double *c, const double *cdot, double *delta);
 int web_gauss_seidel(double hl0, double *z, double *x);
-int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z);   // gs_stream.cu: the five sweeps in one pass
+int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, const double *zin, double *zout, int npanels);   // gs_stream.cu: the five sweeps in one pass
+// the factor applied to z; *res = where the result is (z itself, or x when the sweep ran out of place); x: N words of scratch
+int web_gauss_seidel_to(double hl0, double *z, double *x, double **res);
 // block-grouped reaction factor (jbg = 1): FD blocks at the representative points (unfactored, reference layout)
 void web_jac_groups_launch(const double *c, const double *rewt, double *bd);
 void rbg_add_cj(double *bd, int ns, int nsd, int ngrp, double cj);

@@ -410,24 +410,42 @@ static void gs_launch(const GsArgs &a, int ntile, int t, double *z, double *x, c
 // a square mesh (tests/test_oracle_cpu.py checks this on the matrix), not bit for bit.
 #define GS_OV_BELOW DKB_GS_OV_BELOW
 #define GS_OV_ABOVE DKB_GS_OV_ABOVE
-static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x);
+static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x, bool may_cut = false, bool *moved = nullptr);
 
-int web_gauss_seidel(double hl0, double *z, double *x)
+// z := (approximately) A_S^-1 z.  *res = where the result is: z itself, or x when the sweep ran out of place (several
+// ranks: column panels, gs_stream.cu).  Callers that can read the result from either array (datv, dspigm) use this
+// form; web_gauss_seidel() below keeps the in-place contract of the psol callback.
+int web_gauss_seidel_to(double hl0, double *z, double *x, double **res)
 {
     DkbCtx *c = g_ctx;
     const WebPar &wp = c->web;
-    if (c->nranks <= 1) return gs_sweep(hl0, c->my, true, true, z, x);
+    *res = z;
+    if (c->nranks <= 1) {
+        // DKB_GS_FORCE_PANELS=1 (tests): the column-panel decomposition of the multi-rank path on one GPU
+        const char *fp = getenv("DKB_GS_FORCE_PANELS");
+        if (fp && atoi(fp) == 1) {
+            bool moved = false;
+            const int rc = gs_sweep(hl0, c->my, true, true, z, x, true, &moved);
+            if (moved) *res = x;
+            return rc;
+        }
+        return gs_sweep(hl0, c->my, true, true, z, x);
+    }
     const i64 mxns = (i64)wp.mx * wp.ns;
     const int my_min = wp.my / c->nranks;                    // every slab has at least this many rows
     const int ob = std::min(GS_OV_BELOW, my_min), oa = std::min(GS_OV_ABOVE, my_min);
     const int nb = c->rank > 0 ? ob : 0, na = c->rank < c->nranks - 1 ? oa : 0;
     const i64 n_own = (i64)c->my * mxns;
-    // The solver's vectors carry DKB_GS_OV_BELOW rows of room on both sides (alloc_solver): sweep in place, the overlap
+    // The solver's vectors carry DKB_GS_OV_BELOW rows of room on both sides (alloc_solver): sweep there, the overlap
     // rows arrive straight in that room.  Any other caller's arrays go through a copy.
     auto in_arena = [&](const double *p) { return c->arena && p >= c->arena && p < c->arena + c->arena_doubles; };
     if (in_arena(z) && in_arena(x) && c->halo_pad >= (i64)ob * mxns) {
         slab_overlap_exchange(z, n_own, (i64)ob * mxns, (i64)oa * mxns, z - (i64)nb * mxns, z + n_own);
-        return gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, z - (i64)nb * mxns, x - (i64)nb * mxns);
+        bool moved = false;
+        const int rc = gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, z - (i64)nb * mxns, x - (i64)nb * mxns,
+                                true, &moved);
+        if (moved) *res = x;
+        return rc;
     }
     const i64 need = (i64)(nb + c->my + na) * mxns;
     if (need > c->gs_cap) {
@@ -443,14 +461,27 @@ int web_gauss_seidel(double hl0, double *z, double *x)
     double *zo = c->gs_z + (i64)nb * mxns;
     cudaMemcpyAsync(zo, z, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
     slab_overlap_exchange(z, n_own, (i64)ob * mxns, (i64)oa * mxns, c->gs_z, zo + n_own);
-    const int rc = gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, c->gs_z, c->gs_x);
-    cudaMemcpyAsync(z, zo, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
+    bool moved = false;
+    const int rc = gs_sweep(hl0, nb + c->my + na, c->rank == 0, c->rank == c->nranks - 1, c->gs_z, c->gs_x, true, &moved);
+    cudaMemcpyAsync(z, (moved ? c->gs_x : c->gs_z) + (i64)nb * mxns, sizeof(double) * n_own, cudaMemcpyDeviceToDevice, c->stream);
+    return rc;
+}
+
+int web_gauss_seidel(double hl0, double *z, double *x)
+{
+    DkbCtx *c = g_ctx;
+    double *res = z;
+    const int rc = web_gauss_seidel_to(hl0, z, x, &res);
+    if (rc == 0 && res != z)
+        cudaMemcpyAsync(z, res, sizeof(double) * (size_t)c->my * c->web.mx * c->web.ns, cudaMemcpyDeviceToDevice, c->stream);
     return rc;
 }
 
 // The sweep over `my` rows of z (in place), x = scratch of the same size.  bot_bnd / top_bnd: the first / last row is a
 // domain boundary (mirror coefficients beta2/gamma2 as in the reference); otherwise the neighbour row is simply absent.
-static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x)
+// may_cut (several ranks: the slab sweep is an overlapped decomposition already): the streaming kernel may cut the columns
+// into overlapped panels as well, which needs separate in / out arrays: the result is then in x and *moved = true.
+static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, double *x, bool may_cut, bool *moved)
 {
     DkbCtx *c = g_ctx;
     ProfScope ps(PROF_GS);
@@ -463,9 +494,19 @@ static int gs_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z, d
         const char *st_env = getenv("DKB_GS_STREAM");
         const int ns0 = c->web.ns;
         const bool tiles_ok = ns0 == 2 || ns0 == 4 || ns0 == 6 || ns0 == 8 || ns0 == 10 || ns0 == 12 || ns0 == 16 || ns0 == 20 || ns0 == 24 || ns0 == 32;
-        bool stream = !tiles_ok || 5 * (i64)my >= (i64)c->web.mx;
+        // column panels of ~512 columns (several ranks only; DKB_GS_PANEL_COLS overrides, 0 = none)
+        const char *pc_env = getenv("DKB_GS_PANEL_COLS");
+        const int pcols = pc_env ? atoi(pc_env) : 512;
+        const int npanels = (may_cut && pcols > 0) ? std::max(1, (c->web.mx + pcols / 2) / pcols) : 1;
+        bool stream = !tiles_ok || npanels > 1 || 5 * (i64)my >= (i64)c->web.mx;
         if (st_env) stream = atoi(st_env) != 0 || !tiles_ok;
-        if (stream) return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z);
+        if (stream) {
+            if (npanels > 1) {
+                if (moved) *moved = true;
+                return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z, x, npanels);
+            }
+            return gs_stream_sweep(hl0, my, bot_bnd, top_bnd, z, z, 1);
+        }
     }
     const WebPar &wp = c->web;
     GsArgs a;

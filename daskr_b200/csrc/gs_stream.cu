@@ -48,7 +48,9 @@ __device__ long long gss_dbg[4096 * 8];   // phase clocks of one CTA (the item i
                            // that no floating-point instruction returns (results carry the canonical NaN)
 
 struct GssArgs {
-    int mx, H, nstrips, ng;      // H = rows swept
+    int mx, H, nstrips, ng;      // H = rows swept; nstrips = strips per panel
+    int npanels, pw;             // column panels (see gs_stream_sweep): panel p owns columns [p*pw, (p+1)*pw)
+    int ovl, ovr;                // columns of the neighbouring panels swept redundantly on the left / right
     int bot_bnd, top_bnd;        // first / last row is a domain boundary (mirror coefficient gamma2 = 2*gamma1)
     int s0_last;                 // first step of the last batch (the window is flushed by then)
     i64 hp;                      // exchange slots per (strip boundary, species)
@@ -65,7 +67,7 @@ __device__ __forceinline__ double gss_poll(const double *p)
 // no boundary coefficients).  P[k]: this lane's result of iteration k+1 in the previous step; A1/A2[k]: partial sum
 // after iteration k+1, one / two steps ago.
 template <bool FAST, int SPC>
-__device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int colbase, double b1, double g1, double dinv,
+__device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s, int lane, int colbase, double b1, double g1, double dinv,
                                          double (&P)[5], double (&A1)[4], double (&A2)[4], double *zin_slot, double *zout_slot,
                                          const double *hs_x /*lane 0: exchange slot of this step (x1..x5), or null*/,
                                          const double *hs_a /*lane 0: slot of the previous step (sum1..sum4 at +5)*/,
@@ -89,7 +91,7 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
     for (int k = 5; k >= 1; --k) {
         const int r = s - lane - (k - 1);
         const int ck = colbase - (k - 1);
-        const bool act = FAST || ((unsigned)r < (unsigned)a.H && (unsigned)ck < (unsigned)a.mx);
+        const bool act = FAST || ((unsigned)r < (unsigned)a.H && ck >= xa && ck < xb);   // [xa, xb): columns this panel sweeps
         double rhs;
         if (k == 1) {
             rhs = dinv * zin;                                                  // x = dinv*z (:470-481)
@@ -98,10 +100,10 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
             if (FAST) {
                 rhs = b1 * xr + g1 * xu;
             } else {                                                           // (D-inverse)*U*x (:486-530)
-                const double betU = (ck == 0) ? 2 * b1 : b1;
+                const double betU = (ck == 0) ? 2 * b1 : b1;                    // mirror coefficient at the DOMAIN edge only
                 const double gamU = (r == 0 && a.bot_bnd) ? 2 * g1 : g1;
                 const double t1 = betU * xr, t2 = gamU * xu;
-                const bool has_right = ck < a.mx - 1, lasty = (r == a.H - 1);
+                const bool has_right = ck < xb - 1, lasty = (r == a.H - 1);
                 rhs = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
             }
         }
@@ -111,7 +113,7 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
         } else {
             const double betL = (ck == a.mx - 1) ? 2 * b1 : b1;
             const double gamL = (r == a.H - 1 && a.top_bnd) ? 2 * g1 : g1;
-            if (ck > 0) v = v + betL * S[k - 1];
+            if (ck > xa) v = v + betL * S[k - 1];
             if (r > 0) v = v + gamL * P[k - 1];
         }
         const double sum = (k == 1) ? 0.0 + v : T[k - 2] + v;                  // z := z + x (:568-570), z zeroed at :478
@@ -137,7 +139,7 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int s, int lane, int 
 
 template <int NS, int SPC>
 __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
-                                                            double *__restrict__ z, double *__restrict__ hbuf)
+                                                            const double *zin, double *zout, double *__restrict__ hbuf)
 {
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);   // (PITCH - SPC) odd: the skewed accesses hit 32 different banks
     constexpr int NHL = (GSS_B * GSS_HS + 31) / 32;              // exchange words per lane and batch
@@ -156,19 +158,27 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
         __syncthreads();
         const int item = cur;
         if (item >= total) return;
-        const int I = item / a.ng, g = item - I * a.ng, g0 = g * SPC;
+        // items are numbered strip-major: strip 0 of every panel first, so that a CTA only ever waits for an earlier ticket
+        const int I = item / (a.npanels * a.ng);                 // strip within its panel
+        const int pg = item - I * (a.npanels * a.ng);
+        const int pn = pg / a.ng, g = pg - pn * a.ng, g0 = g * SPC;
+        const int c0 = pn * a.pw, c1 = min(c0 + a.pw, mx);       // columns this panel owns (stores)
+        const int xa = max(c0 - a.ovl, 0), xb = min(c1 + a.ovr, mx);   // columns it sweeps
         const int sp = g0 + w;                                   // this warp's species
         const double b1 = a.beta1[sp], g1 = a.gamma1[sp], dinv = a.dinv[sp];
-        const int colbase = 32 * I + lane;
-        const bool has_prod = I > 0, has_cons = I < a.nstrips - 1;
-        const int cl = 32 * I + pt, cs = 32 * I - 4 + pt;        // columns this thread loads / stores
-        const bool cl_ok = cl < mx, cs_ok = cs >= 0 && cs < mx;
+        const int colbase = xa + 32 * I + lane;
+        const int nst = (xb - xa + 4 + 31) / 32;                 // strips of this panel (the last one may be narrower than the others')
+        const bool has_prod = I > 0, has_cons = I < nst - 1;
+        const bool item_live = I < nst;
+        const int cl = xa + 32 * I + pt, cs = xa + 32 * I - 4 + pt;   // columns this thread loads / stores
+        const bool cl_ok = item_live && cl < xb, cs_ok = item_live && cs >= c0 && cs < c1;
         const i64 offl = (i64)cl * NS + g0 + si, offs = (i64)cs * NS + g0 + si;
-        double *hprod = has_prod ? hbuf + ((i64)(I - 1) * NS + sp) * a.hp * GSS_HS : nullptr;
-        double *hcons = has_cons ? hbuf + ((i64)I * NS + sp) * a.hp * GSS_HS : nullptr;
+        double *hprod = has_prod ? hbuf + (((i64)pn * a.nstrips + I - 1) * NS + sp) * a.hp * GSS_HS : nullptr;
+        double *hcons = has_cons ? hbuf + (((i64)pn * a.nstrips + I) * NS + sp) * a.hp * GSS_HS : nullptr;
         double *hmine = hst + w * (2 * GSS_B * GSS_HS);
+        if (!item_live) continue;                                // a narrower last panel has fewer strips
         // interior strip: every column of every iteration has both neighbours
-        const bool strip_fast = (I >= 1) && (32 * I + 31 <= mx - 2);
+        const bool strip_fast = (I >= 1) && (xa + 32 * I + 31 <= xb - 2);
 
         double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
         double zl[GSS_B], hl[NHL];
@@ -189,7 +199,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
             // ---- z rows [s0+8, s0+16) and the exchange slots of the next batch: loads in flight during the steps ----
             {
                 const int r0 = s0 + GSS_B;
-                const double *src = z + (i64)r0 * mxns + offl;
+                const double *src = zin + (i64)r0 * mxns + offl;
                 if (cl_ok && r0 + GSS_B <= H) {
 #pragma unroll
                     for (int j = 0; j < GSS_B; ++j) zl[j] = GSS_LDZ(src + (i64)j * mxns);
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 #ifndef GSS_NO_STORE
             if (cs_ok && s0 >= 37) {
                 const int r0 = s0 - 44;
-                double *dst = z + (i64)r0 * mxns + offs;
+                double *dst = zout + (i64)r0 * mxns + offs;
                 const double *wsrc = zwin + pt * SPC + si;
                 if (r0 >= 0 && r0 + GSS_B <= H) {
                     double t[GSS_B];
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                         const int s = s0 + j;
                         double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
                         double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
-                        gss_step<true, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                        gss_step<true, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
                                             j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 } else {
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                         double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
                         double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
                         // only the slots the right-hand strip waits for (steps it has an active lane 0 in) are written
-                        gss_step<false, SPC>(a, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                        gss_step<false, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
                                              j ? hsb + (j - 1) * GSS_HS : hsp,
                                              (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
@@ -294,7 +304,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 static int gss_spc(int ns) { return ns % 4 == 0 ? 4 : ns % 5 == 0 ? 5 : ns % 3 == 0 ? 3 : ns % 2 == 0 ? 2 : 1; }
 
 template <int NS, int SPC>
-static int gss_launch(const GssArgs &a, unsigned *ticket, int total, double *z, double *hbuf)
+static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const double *zin, double *zout, double *hbuf)
 {
     DkbCtx *c = g_ctx;
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);
@@ -307,12 +317,18 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, double *z, 
         per_sm = std::max(1, per_sm);
     }
     const int grid = std::min(total, c->nsm * per_sm);
-    gs_stream_kernel<NS, SPC><<<grid, 32 * SPC, smem, c->stream>>>(a, ticket, total, z, hbuf);
+    gs_stream_kernel<NS, SPC><<<grid, 32 * SPC, smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
     return 0;
 }
 
-// z := (approximately) A_S^-1 z over `my` rows, in place.  Same contract as gs_sweep() of gs.cu.
-int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z)
+// zout := (approximately) A_S^-1 zin over `my` rows (zout == zin: in place; required when npanels == 1 is not... see below).
+// npanels > 1: the columns are cut into panels that are swept independently, each extended by `ovl` columns of its left
+// and `ovr` columns of its right neighbour -- the overlapped decomposition the slabs already use in y (gs.cu), for the
+// same reason: the triangular solve couples a point to the columns left of it through paths of total weight
+// <= (beta/(1-gamma))^m over m columns (at most (1/2)^m), the U step reaches one column to the right per iteration.  That
+// shortens the strip pipeline from mx/32 to pw/32 stages, which is what a short, wide slab (8 GPUs) needs.  Panels read
+// columns their neighbours own, so zin and zout must then be different arrays.
+int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, const double *zin, double *zout, int npanels)
 {
     DkbCtx *c = g_ctx;
     const WebPar &wp = c->web;
@@ -330,10 +346,17 @@ int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z)
     }
     const int spc = gss_spc(ns);
     a.ng = ns / spc;
-    a.nstrips = (wp.mx + 4 + 31) / 32;      // iteration k covers columns shifted k-1 to the left: 4 more columns at the right end
+    if (npanels > 1 && zin == zout) return dkb_fail(DKB_E_ARG, "Gauss-Seidel factor: column panels need separate in / out arrays");
+    npanels = std::max(1, std::min(npanels, (wp.mx + 63) / 64));
+    a.pw = (((wp.mx + npanels - 1) / npanels + 31) / 32) * 32;
+    a.npanels = (wp.mx + a.pw - 1) / a.pw;
+    a.ovl = a.npanels > 1 ? 32 : 0;
+    a.ovr = a.npanels > 1 ? 8 : 0;
+    // iteration k covers columns shifted k-1 to the left: 4 more columns at the right end
+    a.nstrips = (std::min(a.pw + a.ovl + a.ovr, wp.mx) + 4 + 31) / 32;
     a.hp = ((i64)(my + 64 + GSS_B - 1) / GSS_B) * GSS_B + 2 * GSS_B;
     a.s0_last = ((my + 36 + GSS_B - 1) / GSS_B) * GSS_B;
-    const size_t hwords = (size_t)std::max(a.nstrips - 1, 1) * ns * a.hp * GSS_HS;
+    const size_t hwords = (size_t)a.npanels * a.nstrips * ns * a.hp * GSS_HS;
     if (hwords > c->gss_hwords) {
         cudaFree(c->gss_hbuf);
         c->gss_hbuf = nullptr;
@@ -347,9 +370,9 @@ int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, double *z)
     if (!c->gss_ticket && cudaMalloc(&c->gss_ticket, sizeof(unsigned)) != cudaSuccess)
         return dkb_fail(DKB_E_CUDA, "Gauss-Seidel factor: cannot allocate the ticket counter");
     cudaMemsetAsync(c->gss_ticket, 0, sizeof(unsigned), c->stream);
-    const int total = a.nstrips * a.ng;
+    const int total = a.nstrips * a.npanels * a.ng;
     int rc = 0;
-#define GSS_CASE(n, s) case n: rc = gss_launch<n, s>(a, c->gss_ticket, total, z, c->gss_hbuf); break;
+#define GSS_CASE(n, s) case n: rc = gss_launch<n, s>(a, c->gss_ticket, total, zin, zout, c->gss_hbuf); break;
     switch (ns) {
         GSS_CASE(1, 1) GSS_CASE(2, 2) GSS_CASE(3, 3) GSS_CASE(4, 4) GSS_CASE(5, 5) GSS_CASE(6, 3) GSS_CASE(7, 1) GSS_CASE(8, 4)
         GSS_CASE(9, 3) GSS_CASE(10, 5) GSS_CASE(11, 1) GSS_CASE(12, 4) GSS_CASE(13, 1) GSS_CASE(14, 2) GSS_CASE(15, 5)

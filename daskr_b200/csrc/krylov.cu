@@ -207,10 +207,10 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
             if (c->ns == 1) {
                 lu_psol_scaled(c->wp, c->iwp, 1, c->npts, A.x, A.wt, A.rsqrtn, v[0], S_RNORM);
             } else if (A.jpre == 3) {   // A_S (Gauss-Seidel, in place on a copy of the rhs) then A_R
-                double *r = v[maxl];
+                double *r = v[maxl], *gsout = r;
                 v_copy(neq, A.x, r);
-                if (web_gauss_seidel(1.0 / A.cj, r, c->wk) != 0) ierr = -1;
-                tpp_psol(c->wp, c->iwp, c->ns, c->npts, r, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
+                if (web_gauss_seidel_to(1.0 / A.cj, r, c->wk, &gsout) != 0) ierr = -1;
+                tpp_psol(c->wp, c->iwp, c->ns, c->npts, gsout, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
             } else {
                 tpp_psol(c->wp, c->iwp, c->ns, c->npts, A.x, nullptr, A.wt, A.rsqrtn, v[0], S_RNORM);
             }

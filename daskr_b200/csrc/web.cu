@@ -441,6 +441,7 @@ int web_datv_fused(const double *v, double vscale, const double *wt, double wsca
 #undef CALL
         }
     }
-    if (jpre != 1 && web_gauss_seidel(1.0 / cj, vtemp, x->wk) != 0) return -1;
-    return tpp_psol(bd, ipbd, w.ns, x->npts, vtemp, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1) != 0 ? -1 : 0;
+    double *gsout = vtemp;   // several ranks: the factor may leave its result in the scratch vector (gs.cu)
+    if (jpre != 1 && web_gauss_seidel_to(1.0 / cj, vtemp, x->wk, &gsout) != 0) return -1;
+    return tpp_psol(bd, ipbd, w.ns, x->npts, gsout, (jpre == 1) ? savr : nullptr, wt, wscale, vnext, -1) != 0 ? -1 : 0;
 }

@@ -32,8 +32,13 @@ def main():
     cases = [("web", 1, 24, 26, True, 1, 0), ("web", 1, 24, 26, False, 1, 0), ("web", 10, 16, 18, True, 1, 0),
              ("heat", 0, 30, 0, True, 1, 0), ("web", 1, 40, 44, True, 3, 0), ("web", 10, 36, 40, True, 3, 0),
              ("web", 1, 40, 44, True, 3, 5), ("web", 2, 30, 33, True, 1, 4),   # last column: block grouping, ng x ng groups
-             ("web", 2, 32, 36, True, 3, 0), ("web", 1, 64, 30, True, 1, 0)]   # mx % 32 == 0: single-kernel datv / residual
+             ("web", 2, 32, 36, True, 3, 0), ("web", 1, 64, 30, True, 1, 0),   # mx % 32 == 0: single-kernel datv / residual
+             ("web", 1, 96, 40, True, 3, -32), ("web", 2, 160, 48, True, 3, -64)]  # ng < 0: Gauss-Seidel column panels of -ng columns
     for kind, np_, mx, my, fused, jpre, ng in cases:
+        os.environ.pop("DKB_GS_PANEL_COLS", None)
+        if ng < 0:
+            os.environ["DKB_GS_PANEL_COLS"] = str(-ng)
+            ng = 0
         if kind == "web":
             touts = [1e-8, 1e-6, 1e-4, 1e-3, 1e-2]
             g = dk.solve_web(np_, mx, my, touts, fused=fused, jpre=jpre, nxg=ng, nyg=ng)

@@ -133,3 +133,25 @@ def test_solve_web_any_block_size(dk, oracle, np_, mx, my, jpre):
     print("np=%d %dx%d jpre=%d: wrms(diff)/tol %s; NST/NLI gpu %s cpu %s" % (np_, mx, my, jpre, err, g["counters"][-1][[10, 19]], o["counters"][-1][[10, 19]]))
     assert err.max() <= 10.0
     assert np.abs(g["counters"][-1][[10, 19]].astype(int) - o["counters"][-1][[10, 19]].astype(int)).max() <= 3
+
+
+@pytest.mark.parametrize("np_,mx,my,pcols", [(1, 96, 40, 32), (2, 200, 33, 64), (10, 1024, 130, 512), (10, 2048, 64, 512), (3, 300, 300, 96)])
+def test_column_panels_reproduce_the_sweep(dk, oracle, np_, mx, my, pcols, monkeypatch):
+    """Several ranks sweep overlapped slabs AND overlapped column panels (32 columns of the left neighbour, 8 of the right
+    one).  Same decay argument as for the slabs; checked here on one GPU (DKB_GS_FORCE_PANELS) against the exact sweep:
+    the owned columns agree to rounding level on the unit square's mesh ratio, far below what a preconditioner needs."""
+    ns = 2 * np_
+    rng = np.random.default_rng(11)
+    b = rng.standard_normal(ns * mx * my)
+    for cj in (2.5e3, 40.0):
+        exact = _gpu_psol(dk, np_, mx, my, 2, cj, b)
+        monkeypatch.setenv("DKB_GS_FORCE_PANELS", "1")
+        monkeypatch.setenv("DKB_GS_PANEL_COLS", str(pcols))
+        cut = _gpu_psol(dk, np_, mx, my, 2, cj, b)
+        monkeypatch.delenv("DKB_GS_FORCE_PANELS")
+        monkeypatch.delenv("DKB_GS_PANEL_COLS")
+        rel = np.abs(cut - exact).max() / np.abs(exact).max()
+        print("%dx%d ns=%d cj=%g panels of %d columns: max |cut - exact| / max|exact| = %.2e" % (mx, my, ns, cj, pcols, rel))
+        # (beta/(1-gamma))^32: ~(1/3)^32 = 5e-16 when dx = dy, up to ~(1/2)^32 = 2e-10 (times a modest constant) when dx << dy
+        assert rel < (1e-12 if mx == my else 1e-7)
+        assert not np.array_equal(cut, exact) or mx <= pcols * 1.5     # the panels were really used
