@@ -62,6 +62,71 @@ __global__ void __launch_bounds__(256) dgefa_kernel(double *bd, int *ipbd, i64 n
 // interleaved in a warp and there are no shuffles.  A thread walks its own contiguous block, so a
 // warp-wide load touches 32 different lines; each 32-byte sector is consumed by 4 consecutive loads
 // of the same thread and stays in L1 in between, which keeps DRAM traffic at one pass over bd.
+// Entries [LO, HI) of one block column (NS doubles at `c`, 32-byte aligned when NS % 4 == 0, 16-byte when NS is even)
+// with the widest aligned loads: the kernel is bound by L1 tag look-ups (every lane of a warp reads a different line),
+// so a 256-bit load moves four entries for the price of one.  Entries outside [LO, HI) of a touched quad are loaded and
+// dropped (they belong to the same column).
+template <int NS, int LO, int HI>
+__device__ __forceinline__ void load_col(const double *__restrict__ c, double (&col)[NS])
+{
+    if constexpr (NS % 4 == 0) {
+#pragma unroll
+        for (int q = LO / 4; q < (HI + 3) / 4; ++q) {
+            double x0, x1, x2, x3;
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x0), "=d"(x1), "=d"(x2), "=d"(x3) : "l"(c + 4 * q));
+            col[4 * q] = x0;
+            col[4 * q + 1] = x1;
+            col[4 * q + 2] = x2;
+            col[4 * q + 3] = x3;
+        }
+    } else if constexpr (NS % 2 == 0) {
+#pragma unroll
+        for (int q = LO / 2; q < (HI + 1) / 2; ++q) {
+            const double2 x = __ldg(reinterpret_cast<const double2 *>(c) + q);
+            col[2 * q] = x.x;
+            col[2 * q + 1] = x.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = LO; i < HI; ++i) col[i] = __ldg(c + i);
+    }
+}
+
+template <int NS, int K>
+__device__ __forceinline__ void tpp_forward(const double *__restrict__ a, const int *__restrict__ pv, double (&b)[NS])
+{
+    if constexpr (K < NS - 1) {
+        const int l = __ldg(pv + K) - 1;
+        double col[NS];
+        load_col<NS, K + 1, NS>(a + K * NS, col);
+        const double bk = b[K];
+        double t = bk;
+#pragma unroll
+        for (int i = K + 1; i < NS; ++i)
+            if (i == l) {
+                t = b[i];
+                b[i] = bk;
+            }
+        b[K] = t;
+#pragma unroll
+        for (int i = K + 1; i < NS; ++i) b[i] = b[i] + t * col[i];
+        tpp_forward<NS, K + 1>(a, pv, b);
+    }
+}
+template <int NS, int K>
+__device__ __forceinline__ void tpp_backward(const double *__restrict__ a, double (&b)[NS])
+{
+    if constexpr (K >= 0) {
+        double col[NS];
+        load_col<NS, 0, K + 1>(a + K * NS, col);
+        b[K] = b[K] / col[K];
+        const double t = -b[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) b[i] = b[i] + t * col[i];
+        tpp_backward<NS, K - 1>(a, b);
+    }
+}
+
 template <int NS>
 __global__ void __launch_bounds__(128) dgesl_tpp_ref_kernel(const double *__restrict__ bd, const int *__restrict__ ipbd,
                                                             i64 nblk, double *__restrict__ bv)
@@ -73,34 +138,8 @@ __global__ void __launch_bounds__(128) dgesl_tpp_ref_kernel(const double *__rest
         double b[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) b[i] = bv[p * NS + i];
-#pragma unroll
-        for (int k = 0; k < NS - 1; ++k) {
-            const int l = __ldg(pv + k) - 1;
-            double col[NS];
-#pragma unroll
-            for (int i = k + 1; i < NS; ++i) col[i] = __ldg(a + k * NS + i);
-            const double bk = b[k];
-            double t = bk;
-#pragma unroll
-            for (int i = k + 1; i < NS; ++i)
-                if (i == l) {
-                    t = b[i];
-                    b[i] = bk;
-                }
-            b[k] = t;
-#pragma unroll
-            for (int i = k + 1; i < NS; ++i) b[i] = b[i] + t * col[i];
-        }
-#pragma unroll
-        for (int k = NS - 1; k >= 0; --k) {
-            double col[NS];
-#pragma unroll
-            for (int i = 0; i <= k; ++i) col[i] = __ldg(a + k * NS + i);
-            b[k] = b[k] / col[k];
-            const double t = -b[k];
-#pragma unroll
-            for (int i = 0; i < k; ++i) b[i] = b[i] + t * col[i];
-        }
+        tpp_forward<NS, 0>(a, pv, b);
+        tpp_backward<NS, NS - 1>(a, b);
 #pragma unroll
         for (int i = 0; i < NS; ++i) bv[p * NS + i] = b[i];
     }
@@ -308,7 +347,13 @@ int lu_dgesl_batched(const double *bd, const int *ipbd, int ns, i64 nblk, double
     cudaStream_t st = g_ctx->stream;
     // measured (tools/bench_extra.py, 1e6 blocks): one thread per block wins for ns <= 2 and ns >= 20,
     // one sub-warp group per block in between
-    if (ns <= 2 || ns >= 20) {
+    static int tpp_min = -1;
+    if (tpp_min < 0) {
+        const char *e = getenv("DKB_DGESL_TPP_MIN");   // tuning hook: smallest ns (> 2) solved by the thread-per-block kernel
+        tpp_min = e ? atoi(e) : 8;
+    }
+    const bool aligned = (reinterpret_cast<uintptr_t>(bd) & 31u) == 0;   // the thread-per-block kernel uses 128 / 256-bit loads
+    if ((ns <= 2 || ns >= tpp_min) && aligned) {
         const int grid = (int)std::min<i64>((nblk + 127) / 128, g_ctx->nsm * 16);
 #define CALL(N) dgesl_tpp_ref_kernel<N><<<grid, 128, 0, st>>>(bd, ipbd, nblk, b)
         NS_DISPATCH(ns, CALL)
