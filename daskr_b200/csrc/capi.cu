@@ -431,12 +431,12 @@ int dkb_init(int device)
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c->d_scal, sizeof(double) * DKB_NSLOT));
     CUDA_TRY(cudaMemset(c->d_scal, 0, sizeof(double) * DKB_NSLOT));
-    CUDA_TRY(cudaMallocHost(&c->h_scal, sizeof(double) * DKB_NSLOT));
+    CUDA_TRY(cudaHostAlloc(&c->h_scal, sizeof(double) * DKB_NSLOT, cudaHostAllocMapped));
     CUDA_TRY(cudaMalloc(&c->d_part, sizeof(double) * DKB_RED_MAXGRID * 8));
     CUDA_TRY(cudaMalloc(&c->d_ticket, sizeof(unsigned)));
     CUDA_TRY(cudaMemset(c->d_ticket, 0, sizeof(unsigned)));
     CUDA_TRY(cudaMalloc(&c->d_iflag, sizeof(int) * 4));
-    CUDA_TRY(cudaMallocHost(&c->h_iflag, sizeof(int) * 4));
+    CUDA_TRY(cudaHostAlloc(&c->h_iflag, sizeof(int) * 4, cudaHostAllocMapped));
     for (int i = 0; i < PROF_NSLOTS; ++i) {
         memset(&c->prof[i], 0, sizeof(ProfSlot));
         strncpy(c->prof[i].name, prof_names[i], sizeof(c->prof[i].name) - 1);
@@ -787,8 +787,7 @@ void dkb_web_res(const double *t, const double *cc, const double *cdot, const do
 static int fetch_first_flag(DkbCtx *c)
 {
     allreduce_min_int(c->d_iflag + 1, 1);
-    cudaMemcpyAsync(c->h_iflag + 1, c->d_iflag + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
+    fetch_words(c->d_iflag + 1, c->h_iflag + 1, sizeof(int));
     dkb_cuda_check("jac");
     return c->h_iflag[1] == INT_MAX ? 0 : c->h_iflag[1];
 }
@@ -823,9 +822,16 @@ void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, doub
         *ierr = fetch_first_flag(c);
         return;
     }
-    web_jac_launch(cc, rewt, *cj, rwp, iwp, c->d_iflag + 1);
+    const bool speculative = web_jac_launch(cc, rewt, *cj, rwp, iwp, c->d_iflag + 1);
     // ierr = dgefa info of the first failing block in the reference; here its block number
     *ierr = fetch_first_flag(c);
+    if (speculative && (*ierr != 0 || c->debug_variant == 16)) {
+        // jac3.cu met a zero pivot (or the test hook asks for this path): its blocks are not LINPACK's from that
+        // elimination step on -- factor again with the kernel that honours linpack.f90:394-397
+        arm_first_flag(c);
+        web_jac_launch(cc, rewt, *cj, rwp, iwp, c->d_iflag + 1, true);
+        *ierr = fetch_first_flag(c);
+    }
 }
 
 // psol, example/example_web.f90:346-391
@@ -1024,8 +1030,7 @@ int dkb_dgefa_batched(double *bd, int *ipbd, int ns, int64_t nblk, int *info, in
     CUDA_TRY(cudaMemcpyAsync(c->d_iflag + 2, c->h_iflag + 2, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     int r = lu_dgefa_batched(bd, ipbd, ns, nblk, info, c->d_iflag + 2);
     if (r) return r;
-    CUDA_TRY(cudaMemcpyAsync(c->h_iflag + 2, c->d_iflag + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fetch_words(c->d_iflag + 2, c->h_iflag + 2, sizeof(int));
     CUDA_TRY(cudaGetLastError());
     if (info_first) *info_first = (c->h_iflag[2] == INT_MAX) ? 0 : c->h_iflag[2];
     return 0;

@@ -234,7 +234,8 @@ void r_axpy_dot(i64 n, double *vnew, const double *vi, double si, int hslot, con
                 int slot);   // vnew -= h*(si*vi) ; out = (sn*vnext).vnew
 void r_axpy_nrm(i64 n, double *vnew, const double *vi, double si, int hslot, int slot);  // vnew -= h*(si*vi) ; out = vnew.vnew
 void r_wrms_parts(i64 n, const double *v, const double *rwt, int slot);        // [sum (v*rwt)^2 , max|v*rwt|]
-void scal_fetch(int slot, int count, double *out);   // stream-ordered D2H + sync
+void scal_fetch(int slot, int count, double *out);   // stream-ordered readback through mapped memory + sync
+void fetch_words(const void *dsrc, void *hdst, size_t bytes);   // same for any few words; hdst in h_scal / h_iflag
 double r_wrms(i64 n, const double *v, const double *rwt);   // ddwnrm :828-868, global N
 double r_nrm2(i64 n, const double *x);
 void allreduce_sum(int slot, int count);
@@ -270,8 +271,9 @@ void web_jac_groups_launch(const double *c, const double *rewt, double *bd);
 void rbg_add_cj(double *bd, int ns, int nsd, int ngrp, double cj);
 int rbg_psol(const double *bd, const int *ipbd, double *b);
 void allreduce_sum_buf(double *buf, i64 n);   // gs.cu: z := GS(A_S) z, x = N words of scratch
-void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd,
-                    int *d_first_flag);
+// returns true if the speculative kernel ran (jac3.cu): a flagged zero pivot then means "run again with exact = true"
+bool web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd,
+                    int *d_first_flag, bool exact = false);
 // fused datv: vnext = wscale*wt * P^-1 ( G(y + v/(wscale*wt), ydot + cj*v/(wscale*wt)) - savr )
 int web_datv_fused(const double *v, double vscale, const double *wt, double wscale, const double *y, const double *ydot,
                    const double *savr, double cj, const double *bd, const int *ipbd, double *vnext, int jpre);

@@ -154,8 +154,7 @@ static int ewt_set(DkbCtx *c, const Tol &tol, const double *y, bool with_vt)
     cudaMemcpyAsync(c->d_iflag, c->h_iflag, sizeof(int), cudaMemcpyHostToDevice, c->stream);
     v_ewt(c->neq, tol.iwt, tol.rtol[0], tol.atol[0], c->d_rtol, c->d_atol, y, c->wt, with_vt ? c->vt : nullptr,
           c->d_id, c->d_iflag);
-    cudaMemcpyAsync(c->h_iflag, c->d_iflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
+    fetch_words(c->d_iflag, c->h_iflag, sizeof(int));
     dkb_cuda_check("ewt_set");
     int bad = c->h_iflag[0];
     if (c->nranks > 1) {
@@ -1376,8 +1375,7 @@ extern "C" void dkb_daskr(dkb_res_t res, const int *neq_, double *t, double *y, 
         c->h_iflag[0] = INT_MAX;
         cudaMemcpyAsync(c->d_iflag, c->h_iflag, sizeof(int), cudaMemcpyHostToDevice, c->stream);
         v_cnst0(neq, c->y, c->d_icnstr, c->d_iflag);
-        cudaMemcpyAsync(c->h_iflag, c->d_iflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-        cudaStreamSynchronize(c->stream);
+        fetch_words(c->d_iflag, c->h_iflag, sizeof(int));
         double bad = (c->h_iflag[0] != INT_MAX) ? 1.0 : 0.0;
         if (c->nranks > 1) {   // every rank must take the same branch
             cudaMemcpyAsync(c->d_scal + 50, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream);

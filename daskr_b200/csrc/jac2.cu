@@ -153,7 +153,7 @@ bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, dou
     case 12: jac2_launch<12>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     case 16: jac2_launch<16>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); return true;
     case 20:
-        switch (g_ctx->debug_variant) {
+        switch (g_ctx->debug_variant - 10) {   // 10..15 select this file (web_jac_launch)
         case 1: jac2_launch<20, 16, true>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
         case 2: jac2_launch<20, 32, false>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;
         case 3: jac2_launch<20, 32, true>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag); break;

@@ -107,8 +107,7 @@ void dkb_jac_rbdpre(const double *t, double *u, const double *r0, dkb_rblock_t r
     cudaMemcpyAsync(c->d_iflag + 2, c->h_iflag + 2, sizeof(int), cudaMemcpyHostToDevice, c->stream);
     int rc = lu_dgefa_batched(bd, ipbd, ns, npts, info, c->d_iflag + 2);
     allreduce_min_int(c->d_iflag + 2, 1);
-    cudaMemcpyAsync(c->h_iflag + 2, c->d_iflag + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
+    fetch_words(c->d_iflag + 2, c->h_iflag + 2, sizeof(int));
     if (rc == 0 && cudaGetLastError() == cudaSuccess) {
         *ierr = 0;
         if (c->h_iflag[2] != INT_MAX && c->h_iflag[2] >= 1 && c->h_iflag[2] <= npts) {   // first failing block (this rank's)

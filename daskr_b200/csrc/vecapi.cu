@@ -102,8 +102,7 @@ int dkb_ewt_set_invert(int64_t n, int iwt, const double *rtol, const double *ato
     CUDA_TRY(cudaMemcpyAsync(c->d_iflag, c->h_iflag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     v_ewt(n, iwt, iwt ? 0.0 : rtol[0], iwt ? 0.0 : atol[0], iwt ? rtol : nullptr, iwt ? atol : nullptr, y, wt, vt, id, c->d_iflag);
     allreduce_min_int(c->d_iflag, 1);   // several ranks: every rank must see the failure (the index is then rank-local at best)
-    CUDA_TRY(cudaMemcpyAsync(c->h_iflag, c->d_iflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    fetch_words(c->d_iflag, c->h_iflag, sizeof(int));
     *ier = (c->h_iflag[0] == INT_MAX) ? 0 : c->h_iflag[0];
     VEC_LEAVE();
 }

@@ -590,11 +590,32 @@ void r_wrms_parts(i64 n, const double *v, const double *rwt, int slot)
     launch_reduce<1, 1>(RWrms{v, rwt}, n, slot);
 }
 
+// Small device -> host readbacks (scalars, flags) do NOT go through a copy engine: a one-warp kernel stores the words
+// into mapped pinned memory and the host waits for the stream.  A cudaMemcpyAsync would queue behind whatever the
+// device-to-host DMA engine is doing -- with DKB_OPT_ASYNC_OUT that is the 16 bytes per unknown of the previous
+// return's y / yprime, and every scalar of the next step waited for it (measured: 119 ms per step at 4096^2 x 20).
+__global__ void mirror_words_kernel(const unsigned *__restrict__ src, unsigned *dst, int n)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+// hdst: inside a cudaHostAlloc'ed (mapped) buffer; the words are valid when this returns
+void fetch_words(const void *dsrc, void *hdst, size_t bytes)
+{
+    DkbCtx *c = g_ctx;
+    void *ddst = nullptr;
+    if (cudaHostGetDevicePointer(&ddst, hdst, 0) != cudaSuccess) {   // not mapped: the copy engine after all
+        cudaGetLastError();
+        cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream);
+    } else {
+        mirror_words_kernel<<<1, 32, 0, c->stream>>>((const unsigned *)dsrc, (unsigned *)ddst, (int)(bytes / 4));
+    }
+    cudaStreamSynchronize(c->stream);
+}
+
 void scal_fetch(int slot, int count, double *out)
 {
     DkbCtx *c = g_ctx;
-    cudaMemcpyAsync(c->h_scal + slot, c->d_scal + slot, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
+    fetch_words(c->d_scal + slot, c->h_scal + slot, sizeof(double) * count);
     dkb_cuda_check("scal_fetch");
     for (int k = 0; k < count; ++k) out[k] = c->h_scal[slot + k];
 }

@@ -337,17 +337,20 @@ void web_res_launch(const double *c, const double *cdot, double *delta)
 #undef CALL
 }
 
-void web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd, int *d_first_flag)
+bool web_jac_launch(const double *c, const double *rewt, double cj, double *bd, int *ipbd, int *d_first_flag, bool exact)
 {
     DkbCtx *x = g_ctx;
     WebDev w = make_webdev();
     const i64 npts = x->npts;
     const int nsd = x->nsd;
-    if (x->debug_variant != 9 && web_jac2(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)) return;   // two-phase kernel (jac2.cu)
+    // debug_variant 9: the one-mapping kernel below; 10..15: jac2.cu (its own variants 0..5 shifted by 10)
+    if (!exact && (x->debug_variant < 9 || x->debug_variant > 15) && web_jac3(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)) return true;   // two rows per lane (jac3.cu)
+    if (x->debug_variant != 9 && web_jac2(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)) return false;   // two-phase kernel (jac2.cu)
 #define CALL(N) web_jac_kernel<N><<<grp_grid(npts, GroupOf<N>::G, 128, 8), 128, 0, x->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag)
     WEB_DISPATCH(w.ns, CALL)
 #undef CALL
     COUNT_LAUNCH();
+    return false;
 }
 
 // ---------------------------------------------------------------- block grouping (jbg = 1)

@@ -19,6 +19,9 @@ bool web_resid_single(const WebDev &w, int mode, const double *v, double vscale,
 // two-phase FD + LU block Jacobian (jac2.cu)
 bool web_jac2(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
               int *d_first_flag);
+// same result, two rows of a point's block per lane for both phases (jac3.cu); false if ns is not instantiated
+bool web_jac3(const WebDev &w, int nsd, const double *c, const double *rewt, double cj, double *bd, int *ipbd,
+              int *d_first_flag);
 // single-kernel datv; returns false if the mesh / ns is not eligible (caller falls back)
 bool web_datv_single(const WebDev &w, const double *v, double vscale, const double *wt, double wscale, const double *y,
                      const double *ydot, const double *savr, double cj, const double *lut, const int *pt,

@@ -259,3 +259,68 @@ def test_dgefa_dgesl_empty_and_single(dk, oracle, ns):
     lu_o, ip_o, info_o = oracle.dgefa_batched(bd, ns)
     assert np.array_equal(lu_g, lu_o) and np.array_equal(ip_g, ip_o) and first == 0
     assert np.array_equal(dk.dgesl_batched(lu_g, ip_g, rhs, ns), oracle.dgesl_batched(lu_o, ip_o, rhs, ns))
+
+
+def _web_jac_gpu(dk, c, rewt, cj, ns, npts, variant=0):
+    """dkb_web_jac through the C ABI with the kernel selector `variant` (option 99: 0 = default, 10 = jac2.cu,
+    9 = the one-mapping kernel, 16 = default kernel followed by the forced exact recomputation)."""
+    from daskr_b200.api import DeviceBuffer, _ref
+
+    L = dk.lib()
+    dk.set_option(99, variant)
+    try:
+        dc, dw = DeviceBuffer.from_host(c), DeviceBuffer.from_host(rewt)
+        dwp, diwp = DeviceBuffer(8 * L.dkb_rbd_lenwp()), DeviceBuffer(4 * L.dkb_rbd_leniwp())
+        dbd, dip = DeviceBuffer(8 * ns * ns * npts), DeviceBuffer(4 * ns * npts)
+        t, cjc, ires, ierr, neq, h = C.c_double(0.0), C.c_double(cj), C.c_int(0), C.c_int(0), C.c_int(c.size), C.c_double(0)
+        ipar = np.array([1, 0], dtype=np.int32)
+        L.dkb_web_jac(None, _ref(ires), _ref(neq), _ref(t), dc.ptr, None, dw.ptr, None, None, _ref(h), _ref(cjc),
+                      dwp.ptr, diwp.ptr, _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+        assert L.dkb_rbd_to_reference(dwp.ptr, diwp.ptr, dbd.ptr, dip.ptr) == 0
+        return dbd.to_host(np.float64, (npts, ns * ns)), dip.to_host(np.int32, (npts, ns)), ierr.value
+    finally:
+        dk.set_option(99, 0)
+
+
+@pytest.mark.parametrize("np_,mx,my", [(10, 16, 12), (10, 35, 7), (11, 6, 5), (12, 9, 4)])
+def test_web_jac_kernel_variants_agree(dk, oracle, np_, mx, my):
+    """ns = 20 / 22 / 24 run jac3.cu (two rows of a block per lane) by default: same blocks and pivots, bit for bit,
+    as the oracle, as jac2.cu, as the one-mapping kernel and as the exact recomputation path."""
+    ns = 2 * np_
+    c, _ = _web_state(oracle, np_, mx, my, seed=3)
+    rewt = 1.0 / (1e-5 * np.abs(c) + 1e-5)
+    cj = 1.0 / 2.1e-3
+    bd_o, ip_o, ierr_o = oracle.web_jac(c, rewt, cj, ns)
+    assert ierr_o == 0
+    _web_setup_gpu(dk, np_, mx, my)
+    for variant in (0, 16, 10, 9):
+        bd_g, ip_g, ierr_g = _web_jac_gpu(dk, c, rewt, cj, ns, mx * my, variant)
+        assert ierr_g == 0, variant
+        assert np.array_equal(ip_g, ip_o), variant
+        assert np.array_equal(bd_g, bd_o), variant
+        assert np.array_equal(np.signbit(bd_g), np.signbit(bd_o)), variant   # zeros keep their sign too
+
+
+@pytest.mark.parametrize("pt", [0, 37])
+def test_web_jac_zero_pivot_is_redone_exactly(dk, oracle, pt):
+    """A block with an exactly zero first pivot: the state of one mesh point is zero (the block is then diagonal) and
+    cj cancels its first diagonal entry to the last bit.  jac3.cu only detects that; the answer must be LINPACK's
+    (linpack.f90:394-397: info = k, the column is skipped, the factorisation goes on) from the exact kernel."""
+    np_, mx, my = 10, 8, 6
+    ns = 2 * np_
+    c, _ = _web_state(oracle, np_, mx, my, seed=5)
+    rewt = 1.0 / (1e-5 * np.abs(c) + 1e-5)
+    c[pt * ns:(pt + 1) * ns] = 0.0
+    rewt[pt * ns:(pt + 1) * ns] = 10.24
+    # the unshifted first diagonal entry exactly as jac_rbdpre forms it: from the oracle with cj = 0
+    bd0, _, _ = oracle.web_jac(c, rewt, 0.0, ns)
+    cj = -bd0[pt, 0]
+    bd_o, ip_o, ierr_o = oracle.web_jac(c, rewt, cj, ns)
+    assert ierr_o != 0
+    _web_setup_gpu(dk, np_, mx, my)
+    bd_g, ip_g, ierr_g = _web_jac_gpu(dk, c, rewt, cj, ns, mx * my, 0)
+    bd_x, ip_x, ierr_x = _web_jac_gpu(dk, c, rewt, cj, ns, mx * my, 10)
+    assert ierr_g != 0 and ierr_g == ierr_x
+    assert np.array_equal(ip_g, ip_x) and np.array_equal(bd_g, bd_x)
+    # the reference stops at the first singular block (daskr_rbdpre.f90:246); up to and including it the factors agree
+    assert np.array_equal(bd_g[:pt + 1], bd_o[:pt + 1]) and np.array_equal(ip_g[:pt + 1], ip_o[:pt + 1])
