@@ -1,6 +1,7 @@
 // capi.cu -- the extern "C" boundary (include/daskr_b200.h): context, setup, built-in
 // problem callbacks, micro-API, NCCL plumbing, profiling.
 #include "dkb_internal.h"
+#include "web_dev.cuh"
 #include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
@@ -1116,6 +1117,33 @@ int dkb_debug_time_datv(int level, int variant, int reps, double *ms)
     c->debug_variant = save_v;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// the residual half of datv (jpre = 3), kernel variant `variant` of web_resid_single
+int dkb_debug_time_resid(int variant, int reps, double *ms)
+{
+    DkbCtx *c = g_ctx;
+    if (!c || !c->arena || c->problem != DKB_PROB_WEB) return dkb_fail(DKB_E_STATE, "needs a food-web solver state");
+    const int save_v = c->debug_variant;
+    c->debug_variant = variant;
+    WebDev w = make_webdev();
+    const double rs = 1.0 / sqrt((double)c->neq_g);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    bool ok = web_resid_single(w, 1, c->v[0], 1.0, c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->z);
+    cudaEventRecord(a, c->stream);
+    for (int i = 0; ok && i < reps; ++i) web_resid_single(w, 1, c->v[0], 1.0, c->wt, rs, c->y, c->yp, c->savr, 1.0e4, c->z);
+    cudaEventRecord(b, c->stream);
+    cudaEventSynchronize(b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, a, b);
+    *ms = t / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    c->debug_variant = save_v;
+    CUDA_TRY(cudaGetLastError());
+    return ok ? 0 : dkb_fail(DKB_E_UNSUPPORTED, "mesh / ns not eligible for the single residual kernel");
 }
 
 int dkb_debug_time_jac(int variant, int reps, double *ms)

@@ -260,6 +260,14 @@ bool web_resid_single(const WebDev &w, int mode, const double *v, double vscale,
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
 #define RS(N) case N: return mode == 1 ? launch_single<N, 4, 4, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out) \
                                        : launch_single<N, 4, 4, 2>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+    if (w.ns == 20 && mode == 1) {   // taller tiles re-read fewer halo rows (6/4, 10/8, 18/16 of the tile from L2)
+        switch (g_ctx->debug_variant) {
+        case 21: return launch_single<20, 8, 2, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+        case 22: return launch_single<20, 16, 1, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+        case 23: return launch_single<20, 8, 3, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
+        default: break;
+        }
+    }
     switch (w.ns) {
         RS(2) RS(4) RS(8) RS(10) RS(12) RS(16) RS(20)
     default: return false;

@@ -22,7 +22,7 @@
 //     results (5 iterates + 4 partial sums per row) in a global exchange buffer (L2 resident); a persistent CTA takes
 //     (strip, species group) items in strip order from a ticket counter, so a CTA only ever waits for a CTA that is
 //     already running (no deadlock for any number of resident CTAs);
-//   * z enters and leaves through a 64-row circular window in shared memory, loaded and stored in coalesced batches of
+//   * z enters and leaves through a 60-row circular window in shared memory, loaded and stored in coalesced batches of
 //     8 rows by the whole CTA (SPC species of 32 points = whole 32-byte sectors), in place: a point's input slot is
 //     reused for its result.
 // Traffic: z read once and written once (16 bytes per unknown) + 2*10/32 words per unknown of strip exchange, instead
@@ -31,7 +31,9 @@
 #include "dkb_internal.h"
 
 #define GSS_B 8        // steps (= rows entering the window) per batch
-#define GSS_WIN 64     // rows of the circular z window
+#define GSS_WIN 60     // rows of the circular z window: rows s0-44 .. s0+15 are live during the batch that starts at step s0
+                       // (60 rows of 36 points x SPC species: three CTAs of four warps per SM; 64 rows left room for two)
+#define GSS_ROW(r) ((unsigned)((r) + 4 * GSS_WIN) % GSS_WIN)   // r >= -GSS_B - 44
 #define GSS_HS 10      // doubles per exchange slot: x1..x5, sum1..sum4 of ONE step of the producer's lane 31, pad (80 bytes, 16-byte aligned)
 #ifdef GSS_DEBUG
 __device__ long long gss_dbg[4096 * 8];   // phase clocks of one CTA (the item in the middle of the schedule), per batch
@@ -53,6 +55,7 @@ struct GssArgs {
     int ovl, ovr;                // columns of the neighbouring panels swept redundantly on the left / right
     int bot_bnd, top_bnd;        // first / last row is a domain boundary (mirror coefficient gamma2 = 2*gamma1)
     int s0_last;                 // first step of the last batch (the window is flushed by then)
+    int edge_fast;               // 0: the edge strips take the fully general step (tuning switch)
     i64 hp;                      // exchange slots per (strip boundary, species)
     double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];
 };
@@ -63,16 +66,20 @@ __device__ __forceinline__ double gss_poll(const double *p)
     return __longlong_as_double((long long)v);
 }
 
-// One step of all five iterations for this lane.  FAST: every lane and iteration is on an interior point (no masks,
-// no boundary coefficients).  P[k]: this lane's result of iteration k+1 in the previous step; A1/A2[k]: partial sum
-// after iteration k+1, one / two steps ago.
-template <bool FAST, int SPC>
+// One step of all five iterations for this lane.  MODE 0: every lane and iteration is on an interior point (no masks,
+// no boundary coefficients).  MODE 1: interior ROWS, any column -- the first and the last strips of a panel, whose
+// column tests do not depend on the step and are hoisted out of the loop by the compiler; these strips head the chain
+// every other strip waits for, so their step time is the period of the whole pipeline.  MODE 2: anything (the first
+// and last batches of every strip).  P[k]: this lane's result of iteration k+1 in the previous step; A1/A2[k]: partial
+// sum after iteration k+1, one / two steps ago.
+template <int MODE, int SPC>
 __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s, int lane, int colbase, double b1, double g1, double dinv,
                                          double (&P)[5], double (&A1)[4], double (&A2)[4], double *zin_slot, double *zout_slot,
                                          const double *hs_x /*lane 0: exchange slot of this step (x1..x5), or null*/,
                                          const double *hs_a /*lane 0: slot of the previous step (sum1..sum4 at +5)*/,
                                          double *hout /*lane 31: slot s-31, or null*/)
 {
+    constexpr bool FAST = MODE == 0, ROWS_IN = MODE <= 1;
     const unsigned full = 0xffffffffu;
     double S[5], T[4];
     double OX[5], OA[4];   // what lane 31 hands to the next strip: never GSS_EMPTY (inactive points hand over 0)
@@ -91,7 +98,8 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
     for (int k = 5; k >= 1; --k) {
         const int r = s - lane - (k - 1);
         const int ck = colbase - (k - 1);
-        const bool act = FAST || ((unsigned)r < (unsigned)a.H && ck >= xa && ck < xb);   // [xa, xb): columns this panel sweeps
+        const bool row_ok = ROWS_IN || (unsigned)r < (unsigned)a.H;
+        const bool act = FAST || (row_ok && ck >= xa && ck < xb);   // [xa, xb): columns this panel sweeps
         double rhs;
         if (k == 1) {
             rhs = dinv * zin;                                                  // x = dinv*z (:470-481)
@@ -101,9 +109,9 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
                 rhs = b1 * xr + g1 * xu;
             } else {                                                           // (D-inverse)*U*x (:486-530)
                 const double betU = (ck == 0) ? 2 * b1 : b1;                    // mirror coefficient at the DOMAIN edge only
-                const double gamU = (r == 0 && a.bot_bnd) ? 2 * g1 : g1;
+                const double gamU = (!ROWS_IN && r == 0 && a.bot_bnd) ? 2 * g1 : g1;
                 const double t1 = betU * xr, t2 = gamU * xu;
-                const bool has_right = ck < xb - 1, lasty = (r == a.H - 1);
+                const bool has_right = ck < xb - 1, lasty = !ROWS_IN && (r == a.H - 1);
                 rhs = has_right ? (lasty ? t1 : t1 + t2) : (lasty ? 0.0 : t2);
             }
         }
@@ -112,9 +120,9 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
             v = (v + b1 * S[k - 1]) + g1 * P[k - 1];
         } else {
             const double betL = (ck == a.mx - 1) ? 2 * b1 : b1;
-            const double gamL = (r == a.H - 1 && a.top_bnd) ? 2 * g1 : g1;
+            const double gamL = (!ROWS_IN && r == a.H - 1 && a.top_bnd) ? 2 * g1 : g1;
             if (ck > xa) v = v + betL * S[k - 1];
-            if (r > 0) v = v + gamL * P[k - 1];
+            if (ROWS_IN || r > 0) v = v + gamL * P[k - 1];
         }
         const double sum = (k == 1) ? 0.0 + v : T[k - 2] + v;                  // z := z + x (:568-570), z zeroed at :478
         if (k == 5) {
@@ -138,7 +146,7 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
 }
 
 template <int NS, int SPC>
-__global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
+__global__ void __launch_bounds__(32 * SPC, (SPC <= 4 ? 3 : 2)) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
                                                             const double *zin, double *zout, double *__restrict__ hbuf)
 {
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);   // (PITCH - SPC) odd: the skewed accesses hit 32 different banks
@@ -226,14 +234,14 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
                 if (r0 >= 0 && r0 + GSS_B <= H) {
                     double t[GSS_B];
 #pragma unroll
-                    for (int j = 0; j < GSS_B; ++j) t[j] = wsrc[((r0 + j) & (GSS_WIN - 1)) * PITCH];
+                    for (int j = 0; j < GSS_B; ++j) t[j] = wsrc[GSS_ROW(r0 + j) * PITCH];
 #pragma unroll
                     for (int j = 0; j < GSS_B; ++j) dst[(i64)j * mxns] = t[j];
                 } else {
 #pragma unroll
                     for (int j = 0; j < GSS_B; ++j) {
                         const int r = r0 + j;
-                        if (r >= 0 && r < H) dst[(i64)j * mxns] = wsrc[(r & (GSS_WIN - 1)) * PITCH];
+                        if (r >= 0 && r < H) dst[(i64)j * mxns] = wsrc[GSS_ROW(r) * PITCH];
                     }
                 }
             }
@@ -241,7 +249,8 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
             GSS_CLK(2);
             // ---- GSS_B steps ----
             if (s0 >= 0 && s0 <= H + 35) {
-                const bool fast = strip_fast && (s0 - 35 >= 1) && (s0 + GSS_B - 1 <= H - 2);
+                const bool rows_in = (s0 - 35 >= 1) && (s0 + GSS_B - 1 <= H - 2);   // rows 1 .. H-2 for every lane and iteration
+                const bool fast = strip_fast && rows_in;
                 const double *hsb = (has_prod && lane == 0) ? hmine + rp * (GSS_B * GSS_HS) : nullptr;
                 const double *hsp = hmine + wp * (GSS_B * GSS_HS) + (GSS_B - 1) * GSS_HS;   // last slot of the previous batch
                 double *hcl = (has_cons && lane == 31) ? hcons : nullptr;
@@ -251,21 +260,30 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 #pragma unroll 2
                     for (int j = 0; j < GSS_B; ++j) {
                         const int s = s0 + j;
-                        double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
-                        double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
-                        gss_step<true, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
-                                            j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
+                        double *zi = zwin + GSS_ROW(s - lane) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + GSS_ROW(s - lane - 4) * PITCH + lane * SPC + w;
+                        gss_step<0, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                         j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
+                    }
+                } else if (rows_in && a.edge_fast) {   // an edge strip away from the first and last rows: every slot of the batch is awaited
+#pragma unroll 1
+                    for (int j = 0; j < GSS_B; ++j) {
+                        const int s = s0 + j;
+                        double *zi = zwin + GSS_ROW(s - lane) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + GSS_ROW(s - lane - 4) * PITCH + lane * SPC + w;
+                        gss_step<1, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                         j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 } else {
 #pragma unroll 1
                     for (int j = 0; j < GSS_B; ++j) {
                         const int s = s0 + j;
-                        double *zi = zwin + ((s - lane) & (GSS_WIN - 1)) * PITCH + (lane + 4) * SPC + w;
-                        double *zo = zwin + ((s - lane - 4) & (GSS_WIN - 1)) * PITCH + lane * SPC + w;
+                        double *zi = zwin + GSS_ROW(s - lane) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + GSS_ROW(s - lane - 4) * PITCH + lane * SPC + w;
                         // only the slots the right-hand strip waits for (steps it has an active lane 0 in) are written
-                        gss_step<false, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
-                                             j ? hsb + (j - 1) * GSS_HS : hsp,
-                                             (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
+                        gss_step<2, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                         j ? hsb + (j - 1) * GSS_HS : hsp,
+                                         (hcl && s >= 31 && s - 31 <= H + 3) ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 }
             }
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(32 * SPC) gs_stream_kernel(const __grid_consta
 #pragma unroll
             for (int j = 0; j < GSS_B; ++j) {
                 const int r = s0 + GSS_B + j;
-                zwin[(r & (GSS_WIN - 1)) * PITCH + (pt + 4) * SPC + si] = zl[j];
+                zwin[GSS_ROW(r) * PITCH + (pt + 4) * SPC + si] = zl[j];
             }
             GSS_CLK(4);
             if (has_prod) {
@@ -316,7 +334,12 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * SPC, smem);
         per_sm = std::max(1, per_sm);
     }
-    const int grid = std::min(total, c->nsm * per_sm);
+    // Two CTAs per SM: the strips form one dependency chain (strip I runs >= 40 steps behind strip I-1), so the time
+    // is (rows + 48 x strips) x the time of ONE warp's step, and a third CTA per SM slows every warp's step by more than
+    // the extra tickets in flight gain (measured 4096^2: 6.3 ms with two, 7.6 ms with three).  debug_variant 31 / 33:
+    // tuning runs with one / three.
+    const int cap = (c->debug_variant >= 31 && c->debug_variant <= 33) ? std::min(per_sm, c->debug_variant - 30) : std::min(per_sm, 2);
+    const int grid = std::min(total, c->nsm * cap);
     gs_stream_kernel<NS, SPC><<<grid, 32 * SPC, smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
     return 0;
 }
@@ -338,6 +361,7 @@ int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, const double
     a.H = my;
     a.bot_bnd = bot_bnd;
     a.top_bnd = top_bnd;
+    a.edge_fast = getenv("DKB_GS_NOEDGE") ? 0 : 1;
     for (int i = 0; i < ns; ++i) {   // :447-457
         const double elamda = 1.0 / (1.0 + 2 * hl0 * (wp.cox[i] + wp.coy[i]));
         a.beta1[i] = hl0 * wp.cox[i] * elamda;

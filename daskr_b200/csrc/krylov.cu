@@ -227,6 +227,7 @@ static void k_dspigm(const GmresArgs &A, int maxl, int kmp, int *ires, int *nres
         *npsol = 1;
         if (ierr != 0) goto L300;
     } else {
+        ProfScope ps(PROF_VEC);
         v_copy(neq, c->dl, v[0]);
         r_dot(neq, v[0], v[0], S_RNORM);
     }
@@ -285,10 +286,13 @@ L120:
 L150:
     *iflag = 1;
     // restart residual dl (irst > 0 always, dslvk:3093)
-    if (kmp == maxl)
-        v_gmres_dl(neq, maxl, v, vs, q, snormw, rnorm * prod, c->dl);
-    else
-        v_scale(neq, rnorm * prod, c->dl);
+    {
+        ProfScope ps(PROF_VEC);
+        if (kmp == maxl)
+            v_gmres_dl(neq, maxl, v, vs, q, snormw, rnorm * prod, c->dl);
+        else
+            v_scale(neq, rnorm * prod, c->dl);
+    }
 
 L200: {
     ll = *lgmr;
@@ -296,6 +300,7 @@ L200: {
     for (int i = 0; i <= ll; ++i) r[i] = 0.0;
     r[0] = rnorm;
     h_dhels(hes, ldh, ll, q, r);
+    ProfScope ps(PROF_VEC);
     v_gmres_solution(neq, ll, v, vs, r, A.wt, A.rsqrtn, A.x, first);
     *rhok = rho;
     return;

@@ -603,7 +603,8 @@ void fetch_words(const void *dsrc, void *hdst, size_t bytes)
 {
     DkbCtx *c = g_ctx;
     void *ddst = nullptr;
-    if (cudaHostGetDevicePointer(&ddst, hdst, 0) != cudaSuccess) {   // not mapped: the copy engine after all
+    static const bool use_dma = getenv("DKB_FETCH_DMA") != nullptr;   // diagnosis: the old path
+    if (use_dma || cudaHostGetDevicePointer(&ddst, hdst, 0) != cudaSuccess) {   // not mapped: the copy engine after all
         cudaGetLastError();
         cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream);
     } else {

@@ -41,3 +41,18 @@ def dk():
     daskr_b200.lib()
     daskr_b200.init(0)
     yield daskr_b200
+
+
+@pytest.fixture(autouse=True)
+def _default_options(request):
+    """Library options are process-wide (like the reference's COMMON blocks): every GPU test starts from the
+    defaults, whatever the test before it left behind -- e.g. solve_web(fused=0) leaves the callback form of datv
+    selected, whose ||v1|| is summed in another order (rounding-level, not bitwise, agreement with the fused form)."""
+    if "dk" in request.fixturenames:
+        d = request.getfixturevalue("dk")
+        d.set_option(d.OPT_FUSED, 2)
+        d.set_option(d.OPT_DEVICE_IO, 0)
+        d.set_option(d.OPT_MAX_STEPS, 0)
+        d.set_option(d.OPT_ASYNC_OUT, 0)
+        d.set_option(99, 0)
+    yield

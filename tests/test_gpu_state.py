@@ -60,7 +60,8 @@ def test_export_import_continues_bitwise(dk, jpre):
     y0, c0 = _run(dk, jpre)
     y1, c1 = _run(dk, jpre, break_after=2)
     assert np.array_equal(c0, c1)
-    assert np.array_equal(y0, y1)
+    bad = np.argwhere(y0 != y1)
+    assert bad.size == 0, "first differences (output, unknown): %s, max |dy| = %.3e" % (bad[:5].tolist(), np.max(np.abs(y0 - y1)))
 
 
 @pytest.mark.parametrize("vector_tol", [False, True])

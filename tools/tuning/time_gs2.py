@@ -19,12 +19,13 @@ ipar = np.array([2, 0], dtype=np.int32)
 def call():
     L.dkb_web_psol(_ref(neq), _ref(t), None, None, None, d_wk.ptr, _ref(cjc), None, None, None, d_b.ptr, _ref(eps),
                    _ref(ierr), None, ipar.ctypes.data_as(C.c_void_p))
+if os.environ.get('GS_VARIANT'): dk.set_option(99, int(os.environ['GS_VARIANT']))
 for _ in range(3): call()
 L.dkb_sync()
 t0 = time.perf_counter()
 for _ in range(20): call()
 L.dkb_sync()
-print("GS %dx%dx20: %%.3f ms per application" % (mx, my) % ((time.perf_counter() - t0) / 20 * 1e3))
+print("GS %dx%dx20 variant %s noedge %s: %%.3f ms per application" % (mx, my, os.environ.get("GS_VARIANT"), os.environ.get("DKB_GS_NOEDGE")) % ((time.perf_counter() - t0) / 20 * 1e3))
 import ctypes
 if hasattr(L, "dkb_debug_gs_clocks"):
     out = (ctypes.c_longlong * 2048)()
