@@ -775,13 +775,32 @@ static void require_problem(int prob, const char *who)
     }
 }
 
+// Several ranks: a residual needs the neighbours' boundary rows, which halo_exchange() writes in front of and behind
+// the vector -- room that only the solver's own vectors have (alloc_solver).  A caller's own device array would be
+// written out of bounds, so it is refused: ires = -2 (DASKR: "stop"), with the reason on stderr.
+static bool halo_ready(const double *v, const char *who, int *ires)
+{
+    DkbCtx *c = g_ctx;
+    if (c->nranks <= 1) return true;
+    const bool in_arena = c->arena && v >= c->arena + c->halo && v + c->neq + c->halo <= c->arena + c->arena_doubles;
+    if (in_arena) {
+        halo_exchange(const_cast<double *>(v));
+        return true;
+    }
+    dkb_fail(DKB_E_ARG, "%s on %d ranks: the state vector must be one of the solver's vectors (they carry room for the "
+                        "neighbours' rows); call it from inside dkb_daskr / on dkb_workspace_get pointers", who, c->nranks);
+    fprintf(stderr, "daskr_b200: %s\n", dkb_last_error());
+    if (ires) *ires = -2;
+    return false;
+}
+
 // res, example/example_web.f90:190-224
 void dkb_web_res(const double *t, const double *cc, const double *cdot, const double *cj, double *delta, int *ires,
                  double *rpar, int *ipar)
 {
-    (void)t; (void)cj; (void)ires; (void)rpar; (void)ipar;
+    (void)t; (void)cj; (void)rpar; (void)ipar;
     require_problem(DKB_PROB_WEB, "dkb_web_res");
-    if (g_ctx->nranks > 1) halo_exchange(const_cast<double *>(cc));
+    if (!halo_ready(cc, "dkb_web_res", ires)) return;
     web_res_launch(cc, cdot, delta);
 }
 
@@ -962,9 +981,9 @@ void dkb_heat_rt(const int *neq, const double *t, const double *u, const double 
 void dkb_heat_res(const double *t, const double *u, const double *udot, const double *cj, double *delta, int *ires,
                   double *rpar, int *ipar)
 {
-    (void)t; (void)cj; (void)ires; (void)rpar; (void)ipar;
+    (void)t; (void)cj; (void)rpar; (void)ipar;
     require_problem(DKB_PROB_HEAT, "dkb_heat_res");
-    if (g_ctx->nranks > 1) halo_exchange(const_cast<double *>(u));
+    if (!halo_ready(u, "dkb_heat_res", ires)) return;
     heat_res_launch(u, udot, delta);
 }
 

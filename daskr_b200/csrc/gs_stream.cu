@@ -145,18 +145,24 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
     }
 }
 
+// CTA = SPC compute warps (one species each) + ONE I/O warp.  The compute warps do nothing but steps: the strips form a
+// dependency chain (strip I runs >= 40 steps behind strip I-1), so the time of the whole sweep is
+// (rows + 48 x strips) x the time of one warp's step, and everything else a compute warp used to do per batch -- z loads,
+// finished rows to memory, polling the exchange words (two thirds of its time, ncu r02_gs_stream) -- sat on that chain.
+// The I/O warp does it for all SPC species while the compute warps run the batch's steps; one barrier per batch.
 template <int NS, int SPC>
-__global__ void __launch_bounds__(32 * SPC, (SPC <= 4 ? 3 : 2)) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
-                                                            const double *zin, double *zout, double *__restrict__ hbuf)
+__global__ void __launch_bounds__(32 * (SPC + 1), 2) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
+                                                                      const double *zin, double *zout, double *__restrict__ hbuf)
 {
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);   // (PITCH - SPC) odd: the skewed accesses hit 32 different banks
-    constexpr int NHL = (GSS_B * GSS_HS + 31) / 32;              // exchange words per lane and batch
+    constexpr int NHL = (GSS_B * GSS_HS + 31) / 32;              // exchange words per lane, species and batch
+    constexpr int HSB = GSS_B * GSS_HS;                          // one staged batch of exchange slots
     extern __shared__ double sm[];
     double *zwin = sm;                                           // [GSS_WIN][PITCH]
-    double *hst = sm + GSS_WIN * PITCH;                          // [SPC][2][GSS_B*GSS_HS]
+    double *hst = sm + GSS_WIN * PITCH;                          // [SPC][3][HSB]: read by this batch / the previous one / being filled
     __shared__ int cur;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int pt = tid / SPC, si = tid - pt * SPC;               // load / store phases: point of the strip row, species of the group
+    const bool io = w == SPC;
     const int mx = a.mx, H = a.H;
     const i64 mxns = (i64)mx * NS;
 
@@ -172,87 +178,132 @@ __global__ void __launch_bounds__(32 * SPC, (SPC <= 4 ? 3 : 2)) gs_stream_kernel
         const int pn = pg / a.ng, g = pg - pn * a.ng, g0 = g * SPC;
         const int c0 = pn * a.pw, c1 = min(c0 + a.pw, mx);       // columns this panel owns (stores)
         const int xa = max(c0 - a.ovl, 0), xb = min(c1 + a.ovr, mx);   // columns it sweeps
-        const int sp = g0 + w;                                   // this warp's species
-        const double b1 = a.beta1[sp], g1 = a.gamma1[sp], dinv = a.dinv[sp];
-        const int colbase = xa + 32 * I + lane;
         const int nst = (xb - xa + 4 + 31) / 32;                 // strips of this panel (the last one may be narrower than the others')
         const bool has_prod = I > 0, has_cons = I < nst - 1;
-        const bool item_live = I < nst;
-        const int cl = xa + 32 * I + pt, cs = xa + 32 * I - 4 + pt;   // columns this thread loads / stores
-        const bool cl_ok = item_live && cl < xb, cs_ok = item_live && cs >= c0 && cs < c1;
-        const i64 offl = (i64)cl * NS + g0 + si, offs = (i64)cs * NS + g0 + si;
-        double *hprod = has_prod ? hbuf + (((i64)pn * a.nstrips + I - 1) * NS + sp) * a.hp * GSS_HS : nullptr;
-        double *hcons = has_cons ? hbuf + (((i64)pn * a.nstrips + I) * NS + sp) * a.hp * GSS_HS : nullptr;
-        double *hmine = hst + w * (2 * GSS_B * GSS_HS);
-        if (!item_live) continue;                                // a narrower last panel has fewer strips
-        // interior strip: every column of every iteration has both neighbours
-        const bool strip_fast = (I >= 1) && (xa + 32 * I + 31 <= xb - 2);
+        if (I >= nst) continue;                                  // a narrower last panel has fewer strips
+        const i64 hstride = a.hp * GSS_HS;                       // exchange words per (strip boundary, species)
+        double *hprod0 = has_prod ? hbuf + (((i64)pn * a.nstrips + I - 1) * NS + g0) * hstride : nullptr;
 
-        double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
-        double zl[GSS_B], hl[NHL];
-#ifdef GSS_DEBUG
-        const bool dbg = (item == total / 2);
-#endif
-
-        // ---- prologue: rows [0, GSS_B) of z and the exchange slots of steps [0, GSS_B) are fetched like every later
-        // batch's (registers now, shared memory at the end of the "batch" s0 = -GSS_B, which has no steps) ----
-        for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
-            const int rp = (s0 / GSS_B) & 1, wp = rp ^ 1;          // exchange staging buffers read by this batch / filled for the next
-#ifdef GSS_DEBUG
-            const int dbgb = min((s0 + GSS_B) / GSS_B, 4095);
-#endif
-            GSS_CLK(0);
-            __syncthreads();
-            GSS_CLK(1);
-            // ---- z rows [s0+8, s0+16) and the exchange slots of the next batch: loads in flight during the steps ----
-            {
-                const int r0 = s0 + GSS_B;
-                const double *src = zin + (i64)r0 * mxns + offl;
-                if (cl_ok && r0 + GSS_B <= H) {
+        if (io) {
+            // ================= I/O warp: lane-flat index f = m*32 + lane over the 32 x SPC (point, species) pairs of a row
+            int fpt[SPC];
+            i64 offl[SPC], offs[SPC];
+            bool cl_ok[SPC], cs_ok[SPC];
 #pragma unroll
-                    for (int j = 0; j < GSS_B; ++j) zl[j] = GSS_LDZ(src + (i64)j * mxns);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < GSS_B; ++j) zl[j] = (cl_ok && r0 + j < H) ? GSS_LDZ(src + (i64)j * mxns) : 0.0;
-                }
+            for (int m = 0; m < SPC; ++m) {
+                const int f = m * 32 + lane, pt = f / SPC, si = f - pt * SPC;
+                const int cl = xa + 32 * I + pt, cs = xa + 32 * I - 4 + pt;   // columns loaded / stored
+                fpt[m] = f;
+                cl_ok[m] = cl < xb;
+                cs_ok[m] = cs >= c0 && cs < c1;
+                offl[m] = (i64)cl * NS + g0 + si;
+                offs[m] = (i64)cs * NS + g0 + si;
             }
-            GSS_CLK(6);
-            if (has_prod) {
+            // z rows travel one batch ahead of their use: rows [s0+16, s0+24) are requested during batch s0, enter the
+            // window during batch s0+8 and are first read by the steps of batch s0+16 -- a whole batch of steps to cover
+            // the DRAM latency.  Before the loop: rows [0, 8).
+            double zl[GSS_B][SPC];
+            auto load_rows = [&](int r0) {
+                const bool whole = r0 + GSS_B <= H;
 #pragma unroll
-                for (int m = 0; m < NHL; ++m) {
-                    const int idx = lane + 32 * m;
-                    hl[m] = (idx < GSS_B * GSS_HS) ? __ldcg(hprod + (i64)(s0 + GSS_B) * GSS_HS + idx) : 0.0;
+                for (int j = 0; j < GSS_B; ++j)
+#pragma unroll
+                    for (int m = 0; m < SPC; ++m)
+                        zl[j][m] = (cl_ok[m] && (whole || r0 + j < H)) ? GSS_LDZ(zin + (i64)(r0 + j) * mxns + offl[m]) : 0.0;
+            };
+            load_rows(0);
+            for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
+                const int bw = ((s0 / GSS_B) + 2) % 3;             // staging buffer filled now, read by the next batch
+                __syncthreads();
+                // ---- rows [s0+8, s0+16) enter the window (read from the next batch on); request the rows after them ----
+#pragma unroll
+                for (int j = 0; j < GSS_B; ++j) {
+                    double *wdst = zwin + GSS_ROW(s0 + GSS_B + j) * PITCH + 4 * SPC;
+#pragma unroll
+                    for (int m = 0; m < SPC; ++m) wdst[fpt[m]] = zl[j][m];
                 }
-            }
-            GSS_CLK(7);
-            // ---- finished rows [s0-44, s0-36) leave the window ----
-#ifndef GSS_NO_STORE
-            if (cs_ok && s0 >= 37) {
-                const int r0 = s0 - 44;
-                double *dst = zout + (i64)r0 * mxns + offs;
-                const double *wsrc = zwin + pt * SPC + si;
-                if (r0 >= 0 && r0 + GSS_B <= H) {
-                    double t[GSS_B];
-#pragma unroll
-                    for (int j = 0; j < GSS_B; ++j) t[j] = wsrc[GSS_ROW(r0 + j) * PITCH];
-#pragma unroll
-                    for (int j = 0; j < GSS_B; ++j) dst[(i64)j * mxns] = t[j];
-                } else {
+                load_rows(s0 + 2 * GSS_B);
+                // ---- finished rows [s0-44, s0-36) leave the window ----
+                if (s0 >= 37) {
+                    const int r0 = s0 - 44;
 #pragma unroll
                     for (int j = 0; j < GSS_B; ++j) {
                         const int r = r0 + j;
-                        if (r >= 0 && r < H) dst[(i64)j * mxns] = wsrc[GSS_ROW(r) * PITCH];
+                        if (r >= 0 && r < H) {
+                            const double *wsrc = zwin + GSS_ROW(r) * PITCH;
+                            double t[SPC];
+#pragma unroll
+                            for (int m = 0; m < SPC; ++m) t[m] = wsrc[fpt[m]];
+#pragma unroll
+                            for (int m = 0; m < SPC; ++m)
+                                if (cs_ok[m]) zout[(i64)r * mxns + offs[m]] = t[m];
+                        }
                     }
                 }
+                if (has_prod) {
+                    // Every exchange word is its own flag: the buffer holds GSS_EMPTY (a NaN no arithmetic produces) until the
+                    // left strip's lane 31 stores the value (one aligned 8-byte store), and goes back to GSS_EMPTY as soon as it
+                    // has been taken.  No fences, no progress counters: a word is either there or not.  All SPC x NHL words
+                    // of this lane are polled together, round after round.
+                    double hl[SPC][NHL];
+                    bool need[SPC][NHL];
+                    bool pending = false;
+#pragma unroll
+                    for (int q = 0; q < SPC; ++q)
+#pragma unroll
+                        for (int m = 0; m < NHL; ++m) {
+                            const int idx = lane + 32 * m;
+                            need[q][m] = idx < HSB && s0 + GSS_B + idx / GSS_HS <= H + 3;
+                            hl[q][m] = __longlong_as_double(GSS_EMPTY);
+                            pending = pending || need[q][m];
+                        }
+                    while (pending) {
+#pragma unroll
+                        for (int q = 0; q < SPC; ++q)
+#pragma unroll
+                            for (int m = 0; m < NHL; ++m)
+                                if (need[q][m] && __double_as_longlong(hl[q][m]) == GSS_EMPTY)
+                                    hl[q][m] = gss_poll(hprod0 + q * hstride + (i64)(s0 + GSS_B) * GSS_HS + lane + 32 * m);
+                        pending = false;
+#pragma unroll
+                        for (int q = 0; q < SPC; ++q)
+#pragma unroll
+                            for (int m = 0; m < NHL; ++m)
+                                pending = pending || (need[q][m] && __double_as_longlong(hl[q][m]) == GSS_EMPTY);
+                        if (pending) __nanosleep(20);
+                    }
+#pragma unroll
+                    for (int q = 0; q < SPC; ++q)
+#pragma unroll
+                        for (int m = 0; m < NHL; ++m)
+                            if (need[q][m]) {
+                                const int idx = lane + 32 * m;
+                                __stcg(hprod0 + q * hstride + (i64)(s0 + GSS_B) * GSS_HS + idx, __longlong_as_double(GSS_EMPTY));
+                                hst[(q * 3 + bw) * HSB + idx] = hl[q][m];
+                            }
+                }
             }
-#endif
-            GSS_CLK(2);
-            // ---- GSS_B steps ----
+            continue;
+        }
+
+        // ================= compute warp w: species g0 + w
+        const int sp = g0 + w;
+        const double b1 = a.beta1[sp], g1 = a.gamma1[sp], dinv = a.dinv[sp];
+        const int colbase = xa + 32 * I + lane;
+        double *hcons = has_cons ? hbuf + (((i64)pn * a.nstrips + I) * NS + sp) * hstride : nullptr;
+        const double *hmine = hst + w * (3 * HSB);
+        // interior strip: every column of every iteration has both neighbours
+        const bool strip_fast = (I >= 1) && (xa + 32 * I + 31 <= xb - 2);
+        double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
+
+        for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
+            const int br = ((s0 / GSS_B) + 1) % 3, bp = ((s0 / GSS_B) + 3) % 3;   // staging buffers of this batch / the previous one
+            __syncthreads();
             if (s0 >= 0 && s0 <= H + 35) {
                 const bool rows_in = (s0 - 35 >= 1) && (s0 + GSS_B - 1 <= H - 2);   // rows 1 .. H-2 for every lane and iteration
                 const bool fast = strip_fast && rows_in;
-                const double *hsb = (has_prod && lane == 0) ? hmine + rp * (GSS_B * GSS_HS) : nullptr;
-                const double *hsp = hmine + wp * (GSS_B * GSS_HS) + (GSS_B - 1) * GSS_HS;   // last slot of the previous batch
+                const double *hsb = (has_prod && lane == 0) ? hmine + br * HSB : nullptr;
+                const double *hsp = hmine + bp * HSB + (GSS_B - 1) * GSS_HS;       // last slot of the previous batch
                 double *hcl = (has_cons && lane == 31) ? hcons : nullptr;
                 // (not unrolled beyond 2: eight inlined steps are ~28 KB of code per path and the warps of an SM sit at
                 // different places in it)
@@ -287,34 +338,6 @@ __global__ void __launch_bounds__(32 * SPC, (SPC <= 4 ? 3 : 2)) gs_stream_kernel
                     }
                 }
             }
-            GSS_CLK(3);
-            // ---- the prefetched rows / slots enter shared memory (read from the next batch on) ----
-#pragma unroll
-            for (int j = 0; j < GSS_B; ++j) {
-                const int r = s0 + GSS_B + j;
-                zwin[GSS_ROW(r) * PITCH + (pt + 4) * SPC + si] = zl[j];
-            }
-            GSS_CLK(4);
-            if (has_prod) {
-                // Every exchange word is its own flag: the buffer holds GSS_EMPTY (a NaN no arithmetic produces) until the
-                // left strip's lane 31 stores the value (one aligned 8-byte store), and goes back to GSS_EMPTY as soon as it
-                // has been taken.  No fences, no progress counters: a word is either there or not.
-#pragma unroll
-                for (int m = 0; m < NHL; ++m) {
-                    const int idx = lane + 32 * m;
-                    const int slot = s0 + GSS_B + idx / GSS_HS;
-                    if (idx < GSS_B * GSS_HS && slot <= H + 3) {
-                        double *src = hprod + (i64)(s0 + GSS_B) * GSS_HS + idx;
-                        while (__double_as_longlong(hl[m]) == GSS_EMPTY) {
-                            __nanosleep(20);
-                            hl[m] = gss_poll(src);
-                        }
-                        __stcg(src, __longlong_as_double(GSS_EMPTY));
-                        hmine[wp * (GSS_B * GSS_HS) + idx] = hl[m];
-                    }
-                }
-            }
-            GSS_CLK(5);
         }
     }
 }
@@ -326,12 +349,12 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
 {
     DkbCtx *c = g_ctx;
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);
-    const size_t smem = sizeof(double) * ((size_t)GSS_WIN * PITCH + (size_t)SPC * 2 * GSS_B * GSS_HS);
+    const size_t smem = sizeof(double) * ((size_t)GSS_WIN * PITCH + (size_t)SPC * 3 * GSS_B * GSS_HS);
     static int per_sm = 0;
     if (!per_sm) {
         cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * SPC, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * (SPC + 1), smem);
         per_sm = std::max(1, per_sm);
     }
     // Two CTAs per SM: the strips form one dependency chain (strip I runs >= 40 steps behind strip I-1), so the time
@@ -340,7 +363,7 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
     // tuning runs with one / three.
     const int cap = (c->debug_variant >= 31 && c->debug_variant <= 33) ? std::min(per_sm, c->debug_variant - 30) : std::min(per_sm, 2);
     const int grid = std::min(total, c->nsm * cap);
-    gs_stream_kernel<NS, SPC><<<grid, 32 * SPC, smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
+    gs_stream_kernel<NS, SPC><<<grid, 32 * (SPC + 1), smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
     return 0;
 }
 

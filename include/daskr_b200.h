@@ -123,7 +123,11 @@ int dkb_web_setpar_ex(int np, int mx, int my, double ay);
 /* res / jac / psol of example_web.f90:190-224, 301-344, 346-391.  As in the example, ipar(1) = jpre selects the
  * preconditioner -- 1: reaction factor A_R (rbdpre / rbgpre), 2: spatial Gauss-Seidel factor A_S, 3: A_S then A_R
  * (the shipped setting), 4: A_R then A_S -- and ipar(2) = jbg selects block grouping (0: dkb_setup_rbdpre,
- * 1: dkb_setup_rbgpre; must match the setup call that was made).  psol uses wk as N words of scratch. */
+ * 1: dkb_setup_rbgpre; must match the setup call that was made).  psol uses wk as N words of scratch.
+ * On several ranks (dkb_comm_init) res exchanges boundary rows with the neighbouring slabs IN PLACE: one mesh row is
+ * written in front of and behind c, room that only the solver's own vectors have (dkb_daskr's workspace,
+ * dkb_workspace_get).  Called on any other array it sets ires = -2 and explains on stderr; the same holds for
+ * dkb_heat_res. */
 void dkb_web_res(const double *t, const double *c, const double *cdot, const double *cj,
                  double *delta, int *ires, double *rpar, int *ipar);
 void dkb_web_jac(dkb_res_t res, int *ires, const int *neq, const double *t, double *c,
