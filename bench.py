@@ -419,7 +419,7 @@ def run_web_bench(args, out_fd):
         jc = P.get("jac", {"ms": 0.0, "count": 0})
         if jc["count"] > 0 and jc["ms"] > 0:
             fl_pt = (ns + 1) * (2 * ns * ns + 3 * ns) + sum(m + 2 * m * m for m in range(1, ns))
-            out["jac_kernel"] = {"kernel": "web_jac2_kernel<20> (FD block Jacobian + LU, incl. the first-failure flag readback)",
+            out["jac_kernel"] = {"kernel": "web_jac3_kernel<20> (FD block Jacobian + LU, two rows of a block per lane; incl. the first-failure flag readback)",
                                  "calls": jc["count"], "avg_ms": jc["ms"] / jc["count"], "flops_per_point": fl_pt,
                                  "achieved_gflops": fl_pt * (neq // ns) / (jc["ms"] / jc["count"] * 1e-3) / 1e9,
                                  "fp64_peak_gflops": {"dfma": 33600.0, "dmul_dadd_pairs_no_fma": 18400.0,

@@ -253,3 +253,34 @@ def test_web_4096_ic_needs_the_spatial_factor(dk):
     assert res[(2048, 1)] >= 0
     assert res[(4096, 3)] >= 0
     assert res[(4096, 1)] == -12
+
+
+def test_web_4096_gauss_seidel_bit_exact(dk, oracle):
+    """The Gauss-Seidel factor at BASELINE configs[3] size (4096 x 4096 x 20): one application of the streaming kernel
+    -- 129 strips per species group, 645 tickets on 296 resident CTAs, the chain of strips two ticket rounds long --
+    array_equal to the oracle's five lexicographic sweeps (example_web.f90:393-575; ~1 min of CPU)."""
+    from daskr_b200.api import DeviceBuffer, _ref
+
+    np_, mx, my, ns = 10, 4096, 4096, 20
+    oracle.web_setup(np_, mx, my)
+    iw = np.zeros(64, dtype=np.int32)
+    dk.setup_rbdpre(mx, my, ns, np_, 0, iw)
+    dk.web_setpar(np_, mx, my)
+    n = ns * mx * my
+    rng = np.random.default_rng(12)
+    zgs = rng.standard_normal(n)
+    cj = 1.0 / 4.2e-5                                    # the step size of the benchmark window
+    L = dk.lib()
+    dz, dwk, dummy = DeviceBuffer.from_host(zgs), DeviceBuffer(zgs.nbytes), DeviceBuffer(64)
+    neq, t, cjc, eps, ierr = C.c_int(n), C.c_double(0.0), C.c_double(cj), C.c_double(0.0), C.c_int(0)
+    ipar2 = np.array([2, 0], dtype=np.int32)             # jpre = 2: the Gauss-Seidel factor alone
+    L.dkb_web_psol(_ref(neq), _ref(t), None, None, None, dwk.ptr, _ref(cjc), None, dummy.ptr, dummy.ptr, dz.ptr, _ref(eps),
+                   _ref(ierr), None, ipar2.ctypes.data_as(C.c_void_p))
+    assert L.dkb_sync() == 0 and ierr.value == 0
+    got = dz.to_host(np.float64, zgs.shape)
+    dz.free()
+    dwk.free()
+    x = np.zeros_like(zgs)
+    oracle.L.o_web_gauss_seidel(n, 1.0 / cj, zgs.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+    del x
+    assert np.array_equal(got, zgs), "max rel diff %.3e" % np.max(np.abs(got - zgs) / np.maximum(np.abs(zgs), 1e-300))
