@@ -62,26 +62,31 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, co
 
     // ---- phase 1: perturbed state for tile + halo (datv:3493-3498)
     // Loads are made unconditional (out-of-range cells read a safe in-tile address and are discarded)
-    // and issued U iterations at a time, so each thread has 4*U independent loads in flight instead
+    // and issued a halo row at a time, so each thread has 4*IT independent loads in flight instead
     // of a load -> divide -> store chain per element.
-    constexpr int NZ = ZY * ZX * NS;
-    constexpr int ITER1 = (NZ + DF_THREADS - 1) / DF_THREADS;
-    constexpr int U = 8;
+    // Row by row: a halo row of the tile is ZX*NS contiguous unknowns in memory, so the flat position e in the row
+    // gives the address by one addition and the place in Z by e + e/NS (the earlier whole-tile flat index cost ~40
+    // integer instructions per element, 40 % of the kernel's instructions in the ncu source view).
+    constexpr int ROWE = ZX * NS;
+    constexpr int IT = (ROWE + DF_THREADS - 1) / DF_THREADS;
     const i64 gsafe = (i64)y0 * mxns + (i64)x0 * NS;   // first unknown of the tile: always in range
-    for (int it0 = 0; it0 < ITER1; it0 += U) {
-        double rwt[U], rv[U], ry[U], ryd[U];
-        int zo[U], yo[U];
+#pragma unroll 1
+    for (int zr = 0; zr < ZY; ++zr) {
+        const int gy = y0 + zr - 1;
+        const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
+        const bool rowyd = zr >= 1 && zr <= DF_TY && gy < w.my;
+        const i64 rbase = (i64)gy * mxns + (i64)(x0 - 1) * NS;      // e = 0 is species 0 of column x0 - 1
+        double rwt[IT], rv[IT], ry[IT], ryd[IT];
+        int zo[IT], yo[IT];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int idx = tid + (it0 + u) * DF_THREADS;
-            const int zr = idx / (ZX * NS), rem = idx - zr * (ZX * NS);
-            const int zx = rem / NS, i = rem - zx * NS;
-            const int gy = y0 + zr - 1, gx = x0 + zx - 1;
-            const bool rowok = (gy >= 0 && gy < w.my) || (gy == -1 && w.has_lo) || (gy == w.my && w.has_hi);
-            const bool ok = (idx < NZ) && rowok && gx >= 0 && gx < w.mx;
-            const bool okyd = ok && i < NPH && zr >= 1 && zr <= DF_TY && zx >= 1 && zx <= DF_TX && gy < w.my;
-            const i64 g = ok ? ((i64)gy * mxns + (i64)gx * NS + i) : gsafe;
-            zo[u] = ok ? (zr * ZX + zx) * PZ + i : -1;
+        for (int u = 0; u < IT; ++u) {
+            const int e = tid + u * DF_THREADS;
+            const int zx = e / NS, i = e - zx * NS;
+            const int gx = x0 + zx - 1;
+            const bool ok = (e < ROWE) && rowok && gx >= 0 && gx < w.mx;
+            const bool okyd = ok && rowyd && i < NPH && zx >= 1 && zx <= DF_TX;
+            const i64 g = ok ? rbase + e : gsafe;
+            zo[u] = ok ? zr * (ZX * PZ) + e + zx : -1;
             yo[u] = okyd ? ((zr - 1) * DF_TX + (zx - 1)) * PY + i : -1;
             rwt[u] = (MODE == 2) ? 1.0 : __ldg(wt + g);
             rv[u] = (MODE == 2) ? 0.0 : __ldg(v + g);
@@ -89,7 +94,7 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, co
             ryd[u] = __ldg(ydot + (okyd ? g : gsafe));
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < IT; ++u) {
             if (zo[u] >= 0) {
                 if (MODE == 2) {
                     Z[zo[u]] = ry[u];

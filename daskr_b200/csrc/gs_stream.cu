@@ -22,7 +22,7 @@
 //     results (5 iterates + 4 partial sums per row) in a global exchange buffer (L2 resident); a persistent CTA takes
 //     (strip, species group) items in strip order from a ticket counter, so a CTA only ever waits for a CTA that is
 //     already running (no deadlock for any number of resident CTAs);
-//   * z enters and leaves through a 60-row circular window in shared memory, loaded and stored in coalesced batches of
+//   * z enters and leaves through a 64-row circular window in shared memory, loaded and stored in coalesced batches of
 //     8 rows by the whole CTA (SPC species of 32 points = whole 32-byte sectors), in place: a point's input slot is
 //     reused for its result.
 // Traffic: z read once and written once (16 bytes per unknown) + 2*10/32 words per unknown of strip exchange, instead
@@ -31,9 +31,9 @@
 #include "dkb_internal.h"
 
 #define GSS_B 8        // steps (= rows entering the window) per batch
-#define GSS_WIN 60     // rows of the circular z window: rows s0-44 .. s0+15 are live during the batch that starts at step s0
-                       // (60 rows of 36 points x SPC species: three CTAs of four warps per SM; 64 rows left room for two)
-#define GSS_ROW(r) ((unsigned)((r) + 4 * GSS_WIN) % GSS_WIN)   // r >= -GSS_B - 44
+#define GSS_WIN 64     // rows of the circular z window (rows s0-44 .. s0+15 are live during the batch that starts at step s0;
+                       // 60 would do and lets three CTAs fit an SM, but three are slower than two -- see gss_launch)
+#define GSS_ROW(r) ((r) & (GSS_WIN - 1))
 #define GSS_HS 10      // doubles per exchange slot: x1..x5, sum1..sum4 of ONE step of the producer's lane 31, pad (80 bytes, 16-byte aligned)
 #ifdef GSS_DEBUG
 __device__ long long gss_dbg[4096 * 8];   // phase clocks of one CTA (the item in the middle of the schedule), per batch
@@ -56,6 +56,7 @@ struct GssArgs {
     int bot_bnd, top_bnd;        // first / last row is a domain boundary (mirror coefficient gamma2 = 2*gamma1)
     int s0_last;                 // first step of the last batch (the window is flushed by then)
     int edge_fast;               // 0: the edge strips take the fully general step (tuning switch)
+    unsigned poll_ns;            // sleep between two polls of the exchange words
     i64 hp;                      // exchange slots per (strip boundary, species)
     double beta1[DKB_NS_MAX], gamma1[DKB_NS_MAX], dinv[DKB_NS_MAX];
 };
@@ -145,13 +146,14 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
     }
 }
 
-// CTA = SPC compute warps (one species each) + ONE I/O warp.  The compute warps do nothing but steps: the strips form a
-// dependency chain (strip I runs >= 40 steps behind strip I-1), so the time of the whole sweep is
-// (rows + 48 x strips) x the time of one warp's step, and everything else a compute warp used to do per batch -- z loads,
-// finished rows to memory, polling the exchange words (two thirds of its time, ncu r02_gs_stream) -- sat on that chain.
-// The I/O warp does it for all SPC species while the compute warps run the batch's steps; one barrier per batch.
+// CTA = SPC compute warps (one species each) + ONE I/O warp (a second one is a tuning option).  The compute warps do
+// nothing but steps: the strips form a dependency chain (strip I runs >= 40 steps behind strip I-1), so the time of the
+// whole sweep is (rows + 48 x strips) x the time of one warp's step, and everything else a compute warp used to do per
+// batch -- z loads, finished rows to memory, polling the exchange words (two thirds of its time, ncu r02_gs_stream) --
+// sat on that chain.  The I/O warp moves the z rows of all SPC species in and out of the window and polls and stages
+// their exchange words while the compute warps run the batch's steps; one barrier per batch.
 template <int NS, int SPC>
-__global__ void __launch_bounds__(32 * (SPC + 1), 2) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
+__global__ void __launch_bounds__(32 * (SPC + 2), 2) gs_stream_kernel(const __grid_constant__ GssArgs a, unsigned *ticket, int total,
                                                                       const double *zin, double *zout, double *__restrict__ hbuf)
 {
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);   // (PITCH - SPC) odd: the skewed accesses hit 32 different banks
@@ -162,7 +164,8 @@ __global__ void __launch_bounds__(32 * (SPC + 1), 2) gs_stream_kernel(const __gr
     double *hst = sm + GSS_WIN * PITCH;                          // [SPC][3][HSB]: read by this batch / the previous one / being filled
     __shared__ int cur;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const bool io = w == SPC;
+    const bool io = w >= SPC, zrole = w == SPC;      // zrole: the z-row warp; the other I/O warp handles the exchange words
+    const bool one_io = blockDim.x == 32 * (SPC + 1);   // launched with a single I/O warp: it does both jobs in turn
     const int mx = a.mx, H = a.H;
     const i64 mxns = (i64)mx * NS;
 
@@ -211,34 +214,37 @@ __global__ void __launch_bounds__(32 * (SPC + 1), 2) gs_stream_kernel(const __gr
                     for (int m = 0; m < SPC; ++m)
                         zl[j][m] = (cl_ok[m] && (whole || r0 + j < H)) ? GSS_LDZ(zin + (i64)(r0 + j) * mxns + offl[m]) : 0.0;
             };
-            load_rows(0);
+            if (zrole) load_rows(0);
             for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
                 const int bw = ((s0 / GSS_B) + 2) % 3;             // staging buffer filled now, read by the next batch
                 __syncthreads();
-                // ---- rows [s0+8, s0+16) enter the window (read from the next batch on); request the rows after them ----
-#pragma unroll
-                for (int j = 0; j < GSS_B; ++j) {
-                    double *wdst = zwin + GSS_ROW(s0 + GSS_B + j) * PITCH + 4 * SPC;
-#pragma unroll
-                    for (int m = 0; m < SPC; ++m) wdst[fpt[m]] = zl[j][m];
-                }
-                load_rows(s0 + 2 * GSS_B);
-                // ---- finished rows [s0-44, s0-36) leave the window ----
-                if (s0 >= 37) {
-                    const int r0 = s0 - 44;
+                if (zrole) {
+                    // ---- rows [s0+8, s0+16) enter the window (read from the next batch on); request the rows after them ----
 #pragma unroll
                     for (int j = 0; j < GSS_B; ++j) {
-                        const int r = r0 + j;
-                        if (r >= 0 && r < H) {
-                            const double *wsrc = zwin + GSS_ROW(r) * PITCH;
-                            double t[SPC];
+                        double *wdst = zwin + GSS_ROW(s0 + GSS_B + j) * PITCH + 4 * SPC;
 #pragma unroll
-                            for (int m = 0; m < SPC; ++m) t[m] = wsrc[fpt[m]];
+                        for (int m = 0; m < SPC; ++m) wdst[fpt[m]] = zl[j][m];
+                    }
+                    load_rows(s0 + 2 * GSS_B);
+                    // ---- finished rows [s0-44, s0-36) leave the window ----
+                    if (s0 >= 37) {
+                        const int r0 = s0 - 44;
 #pragma unroll
-                            for (int m = 0; m < SPC; ++m)
-                                if (cs_ok[m]) zout[(i64)r * mxns + offs[m]] = t[m];
+                        for (int j = 0; j < GSS_B; ++j) {
+                            const int r = r0 + j;
+                            if (r >= 0 && r < H) {
+                                const double *wsrc = zwin + GSS_ROW(r) * PITCH;
+                                double t[SPC];
+#pragma unroll
+                                for (int m = 0; m < SPC; ++m) t[m] = wsrc[fpt[m]];
+#pragma unroll
+                                for (int m = 0; m < SPC; ++m)
+                                    if (cs_ok[m]) zout[(i64)r * mxns + offs[m]] = t[m];
+                            }
                         }
                     }
+                    if (!one_io) continue;
                 }
                 if (has_prod) {
                     // Every exchange word is its own flag: the buffer holds GSS_EMPTY (a NaN no arithmetic produces) until the
@@ -270,7 +276,7 @@ __global__ void __launch_bounds__(32 * (SPC + 1), 2) gs_stream_kernel(const __gr
 #pragma unroll
                             for (int m = 0; m < NHL; ++m)
                                 pending = pending || (need[q][m] && __double_as_longlong(hl[q][m]) == GSS_EMPTY);
-                        if (pending) __nanosleep(20);
+                        if (pending) __nanosleep(a.poll_ns);
                     }
 #pragma unroll
                     for (int q = 0; q < SPC; ++q)
@@ -354,7 +360,7 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
     if (!per_sm) {
         cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * (SPC + 1), smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_stream_kernel<NS, SPC>, 32 * (SPC + 2), smem);
         per_sm = std::max(1, per_sm);
     }
     // Two CTAs per SM: the strips form one dependency chain (strip I runs >= 40 steps behind strip I-1), so the time
@@ -363,7 +369,10 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
     // tuning runs with one / three.
     const int cap = (c->debug_variant >= 31 && c->debug_variant <= 33) ? std::min(per_sm, c->debug_variant - 30) : std::min(per_sm, 2);
     const int grid = std::min(total, c->nsm * cap);
-    gs_stream_kernel<NS, SPC><<<grid, 32 * (SPC + 1), smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
+    // one I/O warp does both jobs; a second one (debug_variant 42: z rows / exchange words split) shortens the I/O warp's
+    // own batch but slows the compute warps it shares schedulers with by more: 6.05 against 5.65 ms at 4096^2
+    const int nio = c->debug_variant == 42 ? 2 : 1;
+    gs_stream_kernel<NS, SPC><<<grid, 32 * (SPC + nio), smem, c->stream>>>(a, ticket, total, zin, zout, hbuf);
     return 0;
 }
 
@@ -385,6 +394,7 @@ int gs_stream_sweep(double hl0, int my, bool bot_bnd, bool top_bnd, const double
     a.bot_bnd = bot_bnd;
     a.top_bnd = top_bnd;
     a.edge_fast = getenv("DKB_GS_NOEDGE") ? 0 : 1;
+    a.poll_ns = getenv("DKB_GS_POLL_NS") ? (unsigned)atoi(getenv("DKB_GS_POLL_NS")) : 20u;
     for (int i = 0; i < ns; ++i) {   // :447-457
         const double elamda = 1.0 / (1.0 + 2 * hl0 * (wp.cox[i] + wp.coy[i]));
         a.beta1[i] = hl0 * wp.cox[i] * elamda;
