@@ -2,7 +2,9 @@ import ctypes as C, sys, numpy as np
 sys.path.insert(0, '/root/repo')
 import daskr_b200 as dk
 dk.init(0)
-np_, mx, my = 10, 1024, 1024
+import os
+M = int(os.environ.get('DATV_MESH', '1024'))
+np_, mx, my = 10, M, M
 ns = 2*np_
 probe = np.zeros(64, dtype=np.int32); dk.setup_rbdpre(mx, my, ns, np_, 0, probe)
 neq = ns*mx*my
@@ -16,6 +18,6 @@ info[10] = 0; dk.set_option(dk.OPT_MAX_STEPS, 3)
 t, idid = dk.daskr(dk.WEB_RES, neq, t, c, cdot, 1.0, info, 1e-5, 1e-5, rwork, iwork, rpar, ipar, dk.WEB_JAC, dk.WEB_PSOL)
 L = dk.lib()
 ms = C.c_double(0)
-for level, var in [(1,0),(2,0),(2,1),(2,2),(2,3),(1,0)]:
+for level, var in [tuple(int(x) for x in lv.split(':')) for lv in os.environ.get('DATV_VARIANTS', '1:0,2:0,2:1,2:2,2:3,1:0').split(',')]:
     rc = L.dkb_debug_time_datv(level, var, 20, C.byref(ms))
     print("level", level, "variant", var, "rc", rc, "ms %.4f" % ms.value, "GB/s %.0f" % (neq*212/ms.value/1e6), flush=True)
