@@ -78,9 +78,11 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
                                          double (&P)[5], double (&A1)[4], double (&A2)[4], double *zin_slot, double *zout_slot,
                                          const double *hs_x /*lane 0: exchange slot of this step (x1..x5), or null*/,
                                          const double *hs_a /*lane 0: slot of the previous step (sum1..sum4 at +5)*/,
-                                         double *hout /*lane 31: slot s-31, or null*/)
+                                         double *hout /*lane 31: slot s-31, or null*/,
+                                         const double *cf = nullptr /*MODE 1: this lane's coefficient table, entry j at cf[32*j]*/,
+                                         bool act5 = true /*MODE 1: the column of iteration 5 belongs to the panel*/)
 {
-    constexpr bool FAST = MODE == 0, ROWS_IN = MODE <= 1;
+    constexpr bool FAST = MODE == 0, TAB = MODE == 1, ROWS_IN = MODE == 1 || MODE == 3;
     const unsigned full = 0xffffffffu;
     double S[5], T[4];
     double OX[5], OA[4];   // what lane 31 hands to the next strip: never GSS_EMPTY (inactive points hand over 0)
@@ -100,7 +102,7 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
         const int r = s - lane - (k - 1);
         const int ck = colbase - (k - 1);
         const bool row_ok = ROWS_IN || (unsigned)r < (unsigned)a.H;
-        const bool act = FAST || (row_ok && ck >= xa && ck < xb);   // [xa, xb): columns this panel sweeps
+        const bool act = FAST || (TAB ? act5 : (row_ok && ck >= xa && ck < xb));   // [xa, xb): columns this panel sweeps
         double rhs;
         if (k == 1) {
             rhs = dinv * zin;                                                  // x = dinv*z (:470-481)
@@ -108,6 +110,8 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
             const double xr = P[k - 2], xu = S[k - 2];                         // iterate k-1 at (c+1,r) and (c,r+1)
             if (FAST) {
                 rhs = b1 * xr + g1 * xu;
+            } else if (TAB) {
+                rhs = cf[32 * (2 * k - 2)] * xr + g1 * xu;                     // coefficient 0 where the reference has no such term
             } else {                                                           // (D-inverse)*U*x (:486-530)
                 const double betU = (ck == 0) ? 2 * b1 : b1;                    // mirror coefficient at the DOMAIN edge only
                 const double gamU = (!ROWS_IN && r == 0 && a.bot_bnd) ? 2 * g1 : g1;
@@ -119,6 +123,8 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
         double v = rhs;                                                        // [(I - (D-inverse)*L)]-inverse (:532-566)
         if (FAST) {
             v = (v + b1 * S[k - 1]) + g1 * P[k - 1];
+        } else if (TAB) {
+            v = (v + cf[32 * (2 * k - 1)] * S[k - 1]) + g1 * P[k - 1];
         } else {
             const double betL = (ck == a.mx - 1) ? 2 * b1 : b1;
             const double gamL = (!ROWS_IN && r == a.H - 1 && a.top_bnd) ? 2 * g1 : g1;
@@ -131,10 +137,10 @@ __device__ __forceinline__ void gss_step(const GssArgs &a, int xa, int xb, int s
         } else {
             A2[k - 1] = A1[k - 1];
             A1[k - 1] = sum;
-            OA[k - 1] = (FAST || act) ? sum : 0.0;
+            OA[k - 1] = (FAST || TAB || act) ? sum : 0.0;
         }
         P[k - 1] = v;
-        OX[k - 1] = (FAST || act) ? v : 0.0;
+        OX[k - 1] = (FAST || TAB || act) ? v : 0.0;
     }
     if (hout != nullptr) {   // lane 31 of a strip with a right neighbour: one 80-byte slot per step, five 16-byte stores
         double2 *h2 = reinterpret_cast<double2 *>(hout);
@@ -162,6 +168,7 @@ __global__ void __launch_bounds__(32 * (SPC + 2), 2) gs_stream_kernel(const __gr
     extern __shared__ double sm[];
     double *zwin = sm;                                           // [GSS_WIN][PITCH]
     double *hst = sm + GSS_WIN * PITCH;                          // [SPC][3][HSB]: read by this batch / the previous one / being filled
+    double *ctab = hst + SPC * 3 * HSB;                          // [SPC][10][32]: edge strips, coefficients per (iteration, lane)
     __shared__ int cur;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool io = w >= SPC, zrole = w == SPC;      // zrole: the z-row warp; the other I/O warp handles the exchange words
@@ -300,6 +307,24 @@ __global__ void __launch_bounds__(32 * (SPC + 2), 2) gs_stream_kernel(const __gr
         const double *hmine = hst + w * (3 * HSB);
         // interior strip: every column of every iteration has both neighbours
         const bool strip_fast = (I >= 1) && (xa + 32 * I + 31 <= xb - 2);
+        // Edge strips (the first one and the last ones of a panel) away from the first / last rows run the interior step
+        // with per-(iteration, lane) coefficients from a table: b1, 2*b1 at a mirrored domain edge, or 0 where the reference
+        // has no left / right term at all (x + 0*y == x up to the sign of a zero).  These strips head the dependency chain,
+        // so their step time is everybody's (the select-based step, MODE 3, has 1.6 times the instructions).  The table
+        // form hands lane 31's values on unmasked, so it needs lane 31 inside the panel whenever there is a consumer.
+        const bool edge_tab = !strip_fast && a.edge_fast && (!has_cons || xa + 32 * I + 27 < xb);
+        double *cf = ctab + w * 320 + lane;
+        bool act5 = true;
+        if (edge_tab) {
+#pragma unroll
+            for (int k = 1; k <= 5; ++k) {
+                const int ck = colbase - (k - 1);
+                cf[32 * (2 * k - 2)] = (ck < xb - 1) ? ((ck == 0) ? 2 * b1 : b1) : 0.0;
+                cf[32 * (2 * k - 1)] = (ck > xa) ? ((ck == a.mx - 1) ? 2 * b1 : b1) : 0.0;
+            }
+            act5 = colbase - 4 >= xa && colbase - 4 < xb;
+            __syncwarp();
+        }
         double P[5] = {0, 0, 0, 0, 0}, A1[4] = {0, 0, 0, 0}, A2[4] = {0, 0, 0, 0};
 
         for (int s0 = -GSS_B; s0 <= a.s0_last; s0 += GSS_B) {
@@ -322,13 +347,22 @@ __global__ void __launch_bounds__(32 * (SPC + 2), 2) gs_stream_kernel(const __gr
                         gss_step<0, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
                                          j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
-                } else if (rows_in && a.edge_fast) {   // an edge strip away from the first and last rows: every slot of the batch is awaited
-#pragma unroll 1
+                } else if (rows_in && edge_tab) {      // an edge strip away from the first and last rows (every slot of the batch is awaited)
+#pragma unroll 2
                     for (int j = 0; j < GSS_B; ++j) {
                         const int s = s0 + j;
                         double *zi = zwin + GSS_ROW(s - lane) * PITCH + (lane + 4) * SPC + w;
                         double *zo = zwin + GSS_ROW(s - lane - 4) * PITCH + lane * SPC + w;
                         gss_step<1, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
+                                         j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr, cf, act5);
+                    }
+                } else if (rows_in && a.edge_fast) {   // same with selects: lane 31 may lie outside the panel
+#pragma unroll 1
+                    for (int j = 0; j < GSS_B; ++j) {
+                        const int s = s0 + j;
+                        double *zi = zwin + GSS_ROW(s - lane) * PITCH + (lane + 4) * SPC + w;
+                        double *zo = zwin + GSS_ROW(s - lane - 4) * PITCH + lane * SPC + w;
+                        gss_step<3, SPC>(a, xa, xb, s, lane, colbase, b1, g1, dinv, P, A1, A2, zi, zo, hsb ? hsb + j * GSS_HS : nullptr,
                                          j ? hsb + (j - 1) * GSS_HS : hsp, hcl ? hcl + (i64)(s - 31) * GSS_HS : nullptr);
                     }
                 } else {
@@ -355,7 +389,7 @@ static int gss_launch(const GssArgs &a, unsigned *ticket, int total, const doubl
 {
     DkbCtx *c = g_ctx;
     constexpr int PITCH = 36 * SPC + ((SPC % 2 == 0) ? 1 : 0);
-    const size_t smem = sizeof(double) * ((size_t)GSS_WIN * PITCH + (size_t)SPC * 3 * GSS_B * GSS_HS);
+    const size_t smem = sizeof(double) * ((size_t)GSS_WIN * PITCH + (size_t)SPC * 3 * GSS_B * GSS_HS + (size_t)SPC * 320);
     static int per_sm = 0;
     if (!per_sm) {
         cudaFuncSetAttribute(gs_stream_kernel<NS, SPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
