@@ -145,7 +145,9 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, co
             const double dcxli = ci - Z[pxl * PZ + k], dcxui = Z[pxu * PZ + k] - ci;
             const double f = c_coy[k] * (dcyui - dcyli) + c_cox[k] * (dcxui - dcxli) + R;   // f:264
             const double d = (k >= NPH) ? -f : (YDT[tid * PY + (k < NPH ? k : 0)] - f);      // res:215-219
-            b[k] = (MODE == 2) ? d : d - __ldg(savr + g0 + k);                     // z = vtemp - savr
+            // z = vtemp - savr (datv:3509).  MODE 1 subtracts in the store phase, where savr is read coalesced (here every
+            // lane would walk its own 160-byte segment: 20 loads of 32 sectors each)
+            b[k] = (MODE == 0) ? d - __ldg(savr + g0 + k) : d;
         }
     }
     __syncthreads();   // Z is free from here on (reused as the output staging buffer)
@@ -192,7 +194,7 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, co
     __syncthreads();
 
     // ---- phase 3: z = z*wght (datv:3518), coalesced rows of 32*ns doubles; NS iterations per
-    // thread, weights loaded up front (unconditionally, clamped) so the loads overlap
+    // thread, weights (MODE 0) / savr (MODE 1) loaded up front (unconditionally, clamped) so the loads overlap
     {
         double rw[NS];
         i64 go[NS];
@@ -202,14 +204,15 @@ web_datv_single_kernel(WebDev w, const double *__restrict__ v, double vscale, co
             const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
             const int oy = y0 + r;
             go[m] = (oy < w.my) ? ((i64)oy * mxns + (i64)x0 * NS + rem) : -1;
-            rw[m] = (MODE != 0) ? 1.0 : __ldg(wt + (go[m] >= 0 ? go[m] : gsafe));
+            rw[m] = (MODE == 2) ? 0.0 : __ldg((MODE == 0 ? wt : savr) + (go[m] >= 0 ? go[m] : gsafe));
         }
 #pragma unroll
         for (int m = 0; m < NS; ++m) {
             const int idx = tid + m * DF_THREADS;
             const int r = idx / (DF_TX * NS), rem = idx - r * (DF_TX * NS);
             const int q = r * DF_TX + rem / NS;
-            if (go[m] >= 0) vnext[go[m]] = (MODE != 0) ? Z[q * PZ + (rem % NS)] : Z[q * PZ + (rem % NS)] * (wscale * rw[m]);
+            const double zv = Z[q * PZ + (rem % NS)];
+            if (go[m] >= 0) vnext[go[m]] = (MODE == 0) ? zv * (wscale * rw[m]) : (MODE == 1) ? zv - rw[m] : zv;
         }
     }
 }
