@@ -30,7 +30,9 @@
 // so the result is bit-identical to the sequential sweeps (tests/test_gpu_gs.py).
 #include "dkb_internal.h"
 
+#ifndef GSS_B
 #define GSS_B 8        // steps (= rows entering the window) per batch
+#endif
 #define GSS_WIN 64     // rows of the circular z window (rows s0-44 .. s0+15 are live during the batch that starts at step s0;
                        // 60 would do and lets three CTAs fit an SM, but three are slower than two -- see gss_launch)
 #define GSS_ROW(r) ((r) & (GSS_WIN - 1))
@@ -234,9 +236,9 @@ __global__ void __launch_bounds__(32 * (SPC + 2), 2) gs_stream_kernel(const __gr
                         for (int m = 0; m < SPC; ++m) wdst[fpt[m]] = zl[j][m];
                     }
                     load_rows(s0 + 2 * GSS_B);
-                    // ---- finished rows [s0-44, s0-36) leave the window ----
+                    // ---- finished rows [s0-36-B, s0-36) leave the window (B = 8: [s0-44, s0-36)) ----
                     if (s0 >= 37) {
-                        const int r0 = s0 - 44;
+                        const int r0 = s0 - 36 - GSS_B;
 #pragma unroll
                         for (int j = 0; j < GSS_B; ++j) {
                             const int r = r0 + j;
