@@ -51,9 +51,21 @@ web_jac3_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
     const double bcoA = __ldg(w.bcoef + l), bcoB = __ldg(w.bcoef + l + L);
     double *sc = s_c[wp][g], *sup = s_up[wp][g], *sfd = s_fd[wp][g];
 
-    for (i64 trip = (i64)blockIdx.x * J3_WARPS + wp; trip < ntrip; trip += (i64)gridDim.x * J3_WARPS) {
+    // The factors leave through a staging buffer in shared memory and are written by the whole CTA, PTS consecutive mesh
+    // points (whole 32-byte sectors) per matrix element.  Stored straight from the LU loop -- 8 bytes per point and
+    // store, 24 bytes per warp -- every store made the L2 fetch its sector first once the array outgrew what the
+    // cache merges: ncu at 4096^2 x 20: 65 GB read and 99 GB written for 55 GB of blocks, 84 ms where 16 x the 1024^2
+    // time is 60.
+    constexpr int PTS = BPW * J3_WARPS, SP = PTS + 1;   // pitch PTS + 1: the rows of a point fall into different banks
+    extern __shared__ double j3_stage[];                // [NSQ][SP] doubles, then [NS][SP] ints
+    int *j3_piv = reinterpret_cast<int *>(j3_stage + NSQ * SP);
+    const int pidx = wp * BPW + (spare ? 0 : g);
+    double *gb = j3_stage + pidx;                       // element e of this lane's point at gb[e * SP]
+
+    for (i64 tb = (i64)blockIdx.x * J3_WARPS; tb < ntrip; tb += (i64)gridDim.x * J3_WARPS) {
+        const i64 trip = tb + wp;
         const i64 p = trip * BPW + (spare ? 0 : g);
-        const bool live = !spare && p < npts;
+        const bool live = !spare && p < npts;            // (a warp past the last group just keeps the CTA's barriers)
         const i64 pp = p < npts ? p : npts - 1;
         // ---- the point's state, increments and -1/del, two species per lane
         {
@@ -120,8 +132,6 @@ web_jac3_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
         }
 
         // ---- phase LU: dgefa with logical row interchanges, two rows per lane
-        const i64 pq = live ? p : 0;
-        double *gb = bd + ((pq >> 5) * NSQ) * 32 + (pq & 31);
         int r0 = l, r1 = l + L;          // LINPACK row currently held in a0 / a1 (columns >= k)
         int ipvA = NS, ipvB = NS;        // ipvt(l+1), ipvt(l+L+1)
         bool zero_pivot = false;
@@ -171,7 +181,7 @@ web_jac3_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
 #pragma unroll
             for (int j = k; j < NS; ++j) {
                 const double src = isB ? a1[j] : a0[j];
-                if (isP && live) gb[(j * NS + k) * 32] = src;
+                if (isP && live) gb[(j * NS + k) * SP] = src;
                 tj[j] = __shfl_sync(FULL, src, pl);
             }
             const double piv = tj[k];
@@ -181,8 +191,8 @@ web_jac3_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
             const double t = -1.0 / piv;
             a0[k] = a0[k] * t;                                        // multipliers (negated); garbage on finished rows
             a1[k] = a1[k] * t;
-            if (live && r0 > k) gb[(k * NS + r0) * 32] = a0[k];
-            if (live && r1 > k) gb[(k * NS + r1) * 32] = a1[k];
+            if (live && r0 > k) gb[(k * NS + r0) * SP] = a0[k];
+            if (live && r1 > k) gb[(k * NS + r1) * SP] = a1[k];
 #pragma unroll
             for (int j = k + 1; j < NS; ++j) {
                 a0[j] = a0[j] + tj[j] * a0[k];
@@ -192,15 +202,30 @@ web_jac3_kernel(WebDev w, int nsd, const double *__restrict__ c, const double *_
         {
             const bool lastB = r1 == NS - 1, lastP = lastB || r0 == NS - 1;
             const double ann = lastB ? a1[NS - 1] : a0[NS - 1];
-            if (lastP && live) gb[((NS - 1) * NS + NS - 1) * 32] = ann;
+            if (lastP && live) gb[((NS - 1) * NS + NS - 1) * SP] = ann;
             zero_pivot = zero_pivot || (lastP && ann == 0.0);
         }
         if (live) {
-            int *ip = ipbd + ((p >> 5) * NS) * 32 + (p & 31);
-            ip[l * 32] = ipvA;
-            ip[(l + L) * 32] = ipvB;
+            j3_piv[l * SP + pidx] = ipvA;
+            j3_piv[(l + L) * SP + pidx] = ipvB;
             if (zero_pivot) atomicMin(first_flag, (int)(p < 2147483646 ? p + 1 : 2147483646));
         }
+        // ---- the CTA's PTS points leave: consecutive threads write consecutive points of one matrix element
+        __syncthreads();
+        {
+            const i64 p0 = tb * BPW;
+            for (int idx = tid; idx < NSQ * PTS; idx += 32 * J3_WARPS) {
+                const int e = idx / PTS, q = idx - e * PTS;
+                const i64 pt = p0 + q;
+                if (pt < npts) bd[((pt >> 5) * NSQ + e) * 32 + (pt & 31)] = j3_stage[e * SP + q];
+            }
+            for (int idx = tid; idx < NS * PTS; idx += 32 * J3_WARPS) {
+                const int e = idx / PTS, q = idx - e * PTS;
+                const i64 pt = p0 + q;
+                if (pt < npts) ipbd[((pt >> 5) * NS + e) * 32 + (pt & 31)] = j3_piv[e * SP + q];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -209,9 +234,12 @@ static void jac3_launch(const WebDev &w, int nsd, const double *c, const double 
                         int *d_first_flag)
 {
     constexpr int BPW = 32 / (NS / 2);
+    constexpr int SP = BPW * J3_WARPS + 1;
+    const size_t smem = sizeof(double) * NS * NS * SP + sizeof(int) * NS * SP;
     static int per_sm = 0;
     if (!per_sm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, web_jac3_kernel<NS, MINB>, 32 * J3_WARPS, 0);
+        cudaFuncSetAttribute(web_jac3_kernel<NS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, web_jac3_kernel<NS, MINB>, 32 * J3_WARPS, smem);
         per_sm = std::max(1, per_sm);
     }
     const i64 npts = (i64)w.mx * w.my;
@@ -219,7 +247,7 @@ static void jac3_launch(const WebDev &w, int nsd, const double *c, const double 
     // grid-stride over point groups: consecutive warps take consecutive groups, so the 32-point tiles of the
     // interleaved layout are completed by warps that run at the same time (the partial sectors meet in L2)
     const int grid = (int)std::min<i64>(nblk, (i64)g_ctx->nsm * per_sm * 8);
-    web_jac3_kernel<NS, MINB><<<grid, 32 * J3_WARPS, 0, g_ctx->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag);
+    web_jac3_kernel<NS, MINB><<<grid, 32 * J3_WARPS, smem, g_ctx->stream>>>(w, nsd, c, rewt, cj, bd, ipbd, d_first_flag);
     g_ctx->launches++;
 }
 
