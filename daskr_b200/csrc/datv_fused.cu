@@ -266,6 +266,7 @@ bool web_resid_single(const WebDev &w, int mode, const double *v, double vscale,
                       const double *ydot, const double *savr, double cj, double *out)
 {
     if (w.mx % DF_TX != 0 || w.np * 2 != w.ns) return false;
+    if (mode == 1 && savr == nullptr) return false;   // mode 1 subtracts savr in its store phase
 #define RS(N) case N: return mode == 1 ? launch_single<N, 4, 4, 1>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out) \
                                        : launch_single<N, 4, 4, 2>(w, v, vscale, wt, wscale, y, ydot, savr, cj, nullptr, nullptr, out);
     if (w.ns == 20 && mode == 1) {   // taller tiles re-read fewer halo rows (6/4, 10/8, 18/16 of the tile from L2)
