@@ -324,3 +324,30 @@ def test_web_jac_zero_pivot_is_redone_exactly(dk, oracle, pt):
     assert np.array_equal(ip_g, ip_x) and np.array_equal(bd_g, bd_x)
     # the reference stops at the first singular block (daskr_rbdpre.f90:246); up to and including it the factors agree
     assert np.array_equal(bd_g[:pt + 1], bd_o[:pt + 1]) and np.array_equal(ip_g[:pt + 1], ip_o[:pt + 1])
+
+
+def test_solve_web_against_an_independent_integrator(dk, oracle):
+    """dkb_daskr on the food web (ns = 2, 8 x 8) against tests/independent.py -- implicit Euler on the DAE with a dense
+    finite-difference Jacobian, extrapolated twice; it shares only the right-hand side with DASKR.  Started from the
+    GPU run's own consistent initial values (output at t = 1e-9)."""
+    from tests.independent import extrapolated_implicit_euler
+
+    np_, mx, my = 1, 8, 8
+    ns = 2 * np_
+    touts = [1e-9, 1e-3, 1e-1, 1.0]
+    for jpre in (1, 3):
+        g = dk.solve_web(np_, mx, my, touts, 1e-8, 1e-8, jpre=jpre)
+        assert g["idid"] == 3
+        if jpre == 1:
+            oracle.web_setup(np_, mx, my)
+            c0 = g["y"][0].copy()
+            pred = (np.arange(c0.size) % ns) >= np_
+
+            def f(c):
+                d, _ = oracle.web_res(c, np.zeros_like(c))
+                return -d
+
+            best = extrapolated_implicit_euler(f, np.where(pred, 0.0, 1.0), c0, touts[0], touts[1:])
+        err = np.max(np.abs(np.asarray(g["y"])[1:] - best) / np.abs(best), axis=1)
+        print("jpre=%d: GPU vs extrapolated implicit Euler at t = 1e-3, 0.1, 1:" % jpre, err)
+        assert err[0] <= 1e-5 and err[1] <= 1e-5 and err[2] <= 1e-7
