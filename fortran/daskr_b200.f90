@@ -13,9 +13,9 @@
 module daskr_b200
    use, intrinsic :: iso_c_binding
    implicit none
-   private :: c_int, c_double, c_int64_t, c_ptr, c_funptr
+   private :: c_int, c_double, c_int64_t, c_ptr, c_funptr, c_char
 
-   integer(c_int), parameter :: DKB_OPT_DEVICE_IO = 1, DKB_OPT_FUSED = 2, DKB_OPT_MAX_STEPS = 3
+   integer(c_int), parameter :: DKB_OPT_DEVICE_IO = 1, DKB_OPT_FUSED = 2, DKB_OPT_MAX_STEPS = 3, DKB_OPT_ASYNC_OUT = 4
 
    abstract interface
       !> res_t, src/daskr_new.f90:11-21 -- y, ydot, delta are device addresses
@@ -48,6 +48,16 @@ module daskr_b200
          real(c_double), intent(inout) :: rpar(*)
          integer(c_int), intent(inout) :: ipar(*)
       end subroutine dkb_psol_t
+      !> rt, src/daskr.f:209-231 (root functions) -- y, yp are device addresses, rval(nrt) is a host array
+      subroutine dkb_rt_t(neq, t, y, yp, nrt, rval, rpar, ipar) bind(C)
+         import :: c_double, c_int, c_ptr
+         integer(c_int), intent(in) :: neq, nrt
+         real(c_double), intent(in) :: t
+         type(c_ptr), value :: y, yp
+         real(c_double), intent(out) :: rval(*)
+         real(c_double), intent(inout) :: rpar(*)
+         integer(c_int), intent(inout) :: ipar(*)
+      end subroutine dkb_rt_t
       !> rblock of jac_rbdpre, src/daskr_rbdpre.f90:176-189, batched over the mesh: r(:) = R(t, u(:)) for all points
       subroutine dkb_rblock_batched_t(t, mx, my, ns, u, r, user) bind(C)
          import :: c_double, c_int, c_ptr
@@ -333,6 +343,136 @@ module daskr_b200
          import :: c_int, c_int64_t, c_ptr
          type(c_ptr), value :: buf
          integer(c_int64_t), value :: nbytes
+         integer(c_int) :: rc
+      end function
+      ! ---- library state, stream, errors ----
+      function dkb_version() bind(C, name="dkb_version") result(v)
+         import :: c_int
+         integer(c_int) :: v
+      end function
+      !> text of the last error (a NUL-terminated C string: convert with c_f_pointer)
+      function dkb_last_error() bind(C, name="dkb_last_error") result(msg)
+         import :: c_ptr
+         type(c_ptr) :: msg
+      end function
+      !> the cudaStream_t every launch of the library goes to (user callbacks enqueue there too)
+      function dkb_stream() bind(C, name="dkb_stream") result(st)
+         import :: c_ptr
+         type(c_ptr) :: st
+      end function
+      function dkb_sync() bind(C, name="dkb_sync") result(rc)
+         import :: c_int
+         integer(c_int) :: rc
+      end function
+      !> DKB_OPT_ASYNC_OUT: block until the y / yprime of the last return have arrived in the caller's (pinned) arrays
+      function dkb_output_wait() bind(C, name="dkb_output_wait") result(rc)
+         import :: c_int
+         integer(c_int) :: rc
+      end function
+
+      ! ---- food web on [0,1] x [0,ay]; heat problem (example/example_heat.f90) ----
+      function dkb_web_setpar_ex(np, mx, my, ay) bind(C, name="dkb_web_setpar_ex") result(rc)
+         import :: c_int, c_double
+         integer(c_int), value :: np, mx, my
+         real(c_double), value :: ay
+         integer(c_int) :: rc
+      end function
+      function dkb_heat_setpar(m) bind(C, name="dkb_heat_setpar") result(rc)
+         import :: c_int
+         integer(c_int), value :: m
+         integer(c_int) :: rc
+      end function
+      function dkb_heat_uinit(u, udot) bind(C, name="dkb_heat_uinit") result(rc)
+         import :: c_int, c_double
+         real(c_double), intent(out) :: u(*), udot(*)
+         integer(c_int) :: rc
+      end function
+      !> res / jac / psol / rt of the heat example: pass c_funloc(dkb_heat_res) etc. to dkb_daskr (never called from Fortran)
+      subroutine dkb_heat_res() bind(C, name="dkb_heat_res")
+      end subroutine
+      subroutine dkb_heat_jac() bind(C, name="dkb_heat_jac")
+      end subroutine
+      subroutine dkb_heat_psol() bind(C, name="dkb_heat_psol")
+      end subroutine
+      subroutine dkb_heat_rt() bind(C, name="dkb_heat_rt")
+      end subroutine
+
+      ! ---- ddot (extern/dblas.f:138) on device vectors ----
+      function dkb_ddot(n, x, y, res) bind(C, name="dkb_ddot") result(rc)
+         import :: c_int, c_int64_t, c_double, c_ptr
+         integer(c_int64_t), value :: n
+         type(c_ptr), value :: x, y
+         real(c_double), intent(out) :: res
+         integer(c_int) :: rc
+      end function
+
+      ! ---- the preconditioner's internal (tile-interleaved) block order and the reference's bd / ipbd ----
+      function dkb_rbd_lenwp() bind(C, name="dkb_rbd_lenwp") result(n)
+         import :: c_int64_t
+         integer(c_int64_t) :: n
+      end function
+      function dkb_rbd_leniwp() bind(C, name="dkb_rbd_leniwp") result(n)
+         import :: c_int64_t
+         integer(c_int64_t) :: n
+      end function
+      function dkb_rbd_to_reference(rwp, iwp, bd, ipbd) bind(C, name="dkb_rbd_to_reference") result(rc)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: rwp, iwp, bd, ipbd
+         integer(c_int) :: rc
+      end function
+      function dkb_rbd_from_reference(bd, ipbd, rwp, iwp) bind(C, name="dkb_rbd_from_reference") result(rc)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: bd, ipbd, rwp, iwp
+         integer(c_int) :: rc
+      end function
+
+      ! ---- device memory helpers, measurement hooks ----
+      function dkb_memcpy_d2d(dst, src, bytes) bind(C, name="dkb_memcpy_d2d") result(rc)
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: dst, src
+         integer(c_int64_t), value :: bytes
+         integer(c_int) :: rc
+      end function
+      function dkb_memset(dst, val, bytes) bind(C, name="dkb_memset") result(rc)
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: dst
+         integer(c_int), value :: val
+         integer(c_int64_t), value :: bytes
+         integer(c_int) :: rc
+      end function
+      function dkb_prof_enable(on) bind(C, name="dkb_prof_enable") result(rc)
+         import :: c_int
+         integer(c_int), value :: on
+         integer(c_int) :: rc
+      end function
+      function dkb_prof_reset() bind(C, name="dkb_prof_reset") result(rc)
+         import :: c_int
+         integer(c_int) :: rc
+      end function
+      !> names: max_entries x 48 characters; ms, launches: max_entries each
+      function dkb_prof_get(names, ms, launches, max_entries) bind(C, name="dkb_prof_get") result(n)
+         import :: c_int, c_int64_t, c_double, c_char
+         character(kind=c_char), intent(out) :: names(*)
+         real(c_double), intent(out) :: ms(*)
+         integer(c_int64_t), intent(out) :: launches(*)
+         integer(c_int), value :: max_entries
+         integer(c_int) :: n
+      end function
+      function dkb_launch_count() bind(C, name="dkb_launch_count") result(n)
+         import :: c_int64_t
+         integer(c_int64_t) :: n
+      end function
+      !> Krylov iterations since dkb_prof_reset by basis index ll = 1..n (dspigm's loop, src/daskr_new.f90:3304-3361)
+      function dkb_krylov_stats(hist, n) bind(C, name="dkb_krylov_stats") result(rc)
+         import :: c_int, c_int64_t
+         integer(c_int64_t), intent(out) :: hist(*)
+         integer(c_int), value :: n
+         integer(c_int) :: rc
+      end function
+      !> dorth's conditional reorthogonalisation (src/daskr_new.f90:3575-3588): branch entered / corrections applied
+      function dkb_reorth_stats(entered, corrections) bind(C, name="dkb_reorth_stats") result(rc)
+         import :: c_int, c_int64_t
+         integer(c_int64_t), intent(out) :: entered, corrections
          integer(c_int) :: rc
       end function
    end interface

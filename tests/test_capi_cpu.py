@@ -133,3 +133,23 @@ def test_block_grouping_tables_and_ownership():
                         jyl, jx = divmod(p, mx)
                         assert jy0 + jyl + 1 == jyr[g // nxg] and jx + 1 == jxr[g % nxg]
             assert (owners == 1).all()
+
+
+def test_fortran_interface_module_covers_the_header():
+    """fortran/daskr_b200.f90 (the ISO_C_BINDING module a Fortran host uses) declares every entry point and callback
+    type of include/daskr_b200.h under its C name, and nothing the header does not have."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "daskr_b200.h")).read()
+    module = open(os.path.join(root, "fortran", "daskr_b200.f90")).read()
+    in_header = set(re.findall(r"\b(dkb_[a-z0-9_]+)\s*\(", header)) | set(re.findall(r"\(\*(dkb_[a-z0-9_]+_t)\)", header))
+    bound = set(re.findall(r"name\s*=\s*[\"'](dkb_[a-z0-9_]+)[\"']", module))
+    abstract = set(re.findall(r"subroutine\s+(dkb_[a-z0-9_]+_t)\s*\(", module))
+    functions = {n for n in in_header if not n.endswith("_t")}
+    assert functions - bound == set(), sorted(functions - bound)
+    assert bound - functions == set(), sorted(bound - functions)
+    callbacks = {n for n in in_header if n.endswith("_t")}
+    # the batched rblock type carries a longer name on the Fortran side
+    assert callbacks - abstract - {"dkb_rblock_t"} == set(), sorted(callbacks - abstract)
+    assert "dkb_rblock_batched_t" in abstract
